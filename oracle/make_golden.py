@@ -1,0 +1,434 @@
+"""
+TEST INFRASTRUCTURE, CONTAINER-ONLY: generates tests/golden/*.npz by running the
+UNMODIFIED reference (via oracle/ref_harness.py) under injected noise.
+
+    python oracle/make_golden.py            # rewrites every fixture (about 2 min)
+
+The reference holds no known-answer trajectories, so these
+fixtures ARE the pins for the C oracle (oracle/yagre_oracle.c) and, through it
+and directly, for the CUDA path.  Each .npz carries the lowered problem
+(exactly the arrays the C-ABI takes), the injected noise, and the reference's
+outputs: trajectory, accept decisions, log-posterior per level along the
+trajectory, Welford mean / marginal variance where FullDiagnostics was used.
+
+Constants are those of the BASELINE.json configs:
+  C1 example_mcmc_1d.py:12-30              C2 example_mcmc_2d_singleLevel.py:19-27
+  2-D two level example_mcmc_2d_twoLevel.py:10-40
+  C3 example_inference_linearModel_twoLevel.py:33-74,128-129,173
+  C4/C5 example_inference_lotkaVolterra_{single,two}Level.py:29-106
+"""
+import json
+import os
+import sys
+
+import numpy as np
+from numpy.random import Generator, Philox
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as rh   # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+# --------------------------------------------------------------------------
+# lowering helpers: reference objects -> plain arrays (what the C-ABI takes)
+# --------------------------------------------------------------------------
+
+def lower_proposal(kind, value, dim):
+    """Lower-triangular factor L with p = s + L z.  Diagonal kinds mimic
+    DiagonalCovarianceMatrix exactly: it stores reciprocal(var) and applies
+    sqrt(reciprocal(precision)) (covariance.py:37-38,51-52)."""
+    if kind == 'iid':
+        var = np.full(dim, float(value))
+        return np.diag(np.sqrt(np.reciprocal(np.reciprocal(var))))
+    if kind == 'diag':
+        var = np.asarray(value, dtype=np.float64)
+        return np.diag(np.sqrt(np.reciprocal(np.reciprocal(var))))
+    if kind == 'dense':
+        from scipy.linalg import cholesky
+        return cholesky(np.asarray(value, dtype=np.float64), lower=True)   # covariance.py:78
+    raise ValueError(kind)
+
+
+def diag_precision(var, dim):
+    """IID/Diagonal covariance -> dense precision matrix with exact zeros off
+    the diagonal (covariance.py:37-38,54-55)."""
+    var = np.full(dim, float(var)) if np.ndim(var) == 0 else np.asarray(var, dtype=np.float64)
+    return np.diag(np.reciprocal(var))
+
+
+def make_noise(rng, nChains, nSteps, J, d, zero_at=(), u_edge=True):
+    z = rng.standard_normal((nChains, nSteps, J, d))
+    u_c = rng.random((nChains, nSteps, J))
+    u_f = rng.random((nChains, nSteps))
+    for (c, n, j) in zero_at:           # equality-skip edge cases (metropolisHastings.py:60-61)
+        if j is None:
+            z[c, n, :, :] = 0.0
+        else:
+            z[c, n, j, :] = 0.0
+    if u_edge and nSteps > 12:
+        u_f[0, 5] = 0.0                 # u == 0 accepts whenever a >= 0
+        u_f[0, 9] = np.nextafter(1.0, 0.0)
+        u_c[0, 7, 0] = 0.0
+    return z, u_c, u_f
+
+
+def logpost_along(target, stateType, traj):
+    cache = {}
+    out = np.empty(len(traj))
+    for i, s in enumerate(traj):
+        key = s.tobytes()
+        if key not in cache:
+            cache[key] = float(np.asarray(target.evaluate_log(stateType(s.copy()))).reshape(-1)[0])
+        out[i] = cache[key]
+    return out
+
+
+def save(name, meta, arrays):
+    os.makedirs(OUT, exist_ok=True)
+    arrays = {k: np.asarray(v) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **arrays)
+    print(f"  wrote {name}.npz  ({sum(a.nbytes for a in arrays.values())/1024:.0f} KiB raw)")
+
+
+# --------------------------------------------------------------------------
+# Gaussian explicit targets
+# --------------------------------------------------------------------------
+
+def gauss2d_level_arrays(mean, cov):
+    from scipy.stats import multivariate_normal
+    mean = np.asarray(mean, dtype=np.float64)
+    cov = np.asarray(cov, dtype=np.float64)
+    prec = np.linalg.inv(cov)
+    prec = 0.5 * (prec + prec.T)
+    # scipy's logpdf = -0.5*(d log 2pi + logdet) - 0.5 maha   (testSetup.py:36-40)
+    logconst = float(multivariate_normal(mean, cov).logpdf(mean))
+    return mean, prec, logconst
+
+
+def case_gauss1d():
+    nChains, nSteps = 3, 300
+    rng = Generator(Philox(101))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, 1, zero_at=[(1, 20, 0)])
+    tgt = rh.GaussianTargetDensity1d(rh.ScalarParameter(np.array([1.5])), 1.)
+    propVar = 1.5
+    traj, acc, lp, wm, wv = [], [], [], [], []
+    for c in range(nChains):
+        inj = rh.NoiseInjector(z[c], None, u_f[c])
+        mcmc = rh.quiet(rh.MetropolisedRandomWalk, tgt, rh.IIDCovarianceMatrix(1, propVar), rh.FullDiagnostics())
+        t, a = rh.run_reference_chain(mcmc, rh.ScalarParameter(np.array([-3.])), nSteps, inj, False)
+        traj.append(t); acc.append(a)
+        lp.append(logpost_along(tgt, rh.ScalarParameter, t))
+        wm.append(np.asarray(mcmc.diagnostics.mean()).reshape(-1))
+        wv.append(np.asarray(mcmc.diagnostics.marginal_variance()).reshape(-1))
+    meta = dict(model='gauss', dim=1, levels=1, J=1, eq='isclose',
+                note='C1 example_mcmc_1d.py:12-30; ScalarParameter equality is math.isclose (scalar.py:38-43)')
+    save("mrw_gauss1d", meta, dict(
+        prop_L=lower_proposal('iid', propVar, 1),
+        L0_g_mean=[1.5], L0_g_prec=[[1.0]], L0_g_logconst=0.0,
+        theta0=np.full((nChains, 1), -3.0), z=z, u_c=u_c, u_f=u_f,
+        traj=traj, accepted=acc, logpost_L0=lp, welford_mean=wm, welford_var=wv))
+
+
+TGT_MEAN = np.array([1., 1.5])
+TGT_COV = np.array([[2.4, -0.5], [-0.5, 0.7]])
+
+
+def case_gauss2d(name, propKind, propValue, seed):
+    nChains, nSteps = 3, 300
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, 2, zero_at=[(2, 11, 0)])
+    tgt = rh.GaussianTargetDensity2d(rh.ParameterVector(TGT_MEAN), TGT_COV)
+    traj, acc, lp, wm, wv = [], [], [], [], []
+    for c in range(nChains):
+        inj = rh.NoiseInjector(z[c], None, u_f[c])
+        b = rh.MRWBuilder()
+        b.explicitTarget = tgt
+        b.proposalCovariance = rh.covariance_from_spec(propKind, propValue, 2)
+        b.diagnostics = rh.FullDiagnostics()
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.array([-8., -7.])), nSteps, inj, False)
+        traj.append(t); acc.append(a)
+        lp.append(logpost_along(tgt, rh.ParameterVector, t))
+        wm.append(mcmc.diagnostics.mean()); wv.append(mcmc.diagnostics.marginal_variance())
+    m, P, lc = gauss2d_level_arrays(TGT_MEAN, TGT_COV)
+    meta = dict(model='gauss', dim=2, levels=1, J=1, eq='exact',
+                note=f'C2 example_mcmc_2d_singleLevel.py:19-27, proposal {propKind}')
+    save(name, meta, dict(
+        prop_L=lower_proposal(propKind, propValue, 2),
+        L0_g_mean=m, L0_g_prec=P, L0_g_logconst=lc,
+        theta0=np.tile([-8., -7.], (nChains, 1)), z=z, u_c=u_c, u_f=u_f,
+        traj=traj, accepted=acc, logpost_L0=lp, welford_mean=wm, welford_var=wv))
+
+
+def case_mlda_gauss2d():
+    nChains, nSteps, J = 3, 250, 6
+    rng = Generator(Philox(303))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2,
+                             zero_at=[(0, 3, None), (1, 14, 2), (2, 30, None)])
+    surMean = TGT_MEAN + np.array([0.15, -0.2])
+    surCov = 2. * TGT_COV + np.array([[0.1, 1.2], [1.2, 0.05]])
+    tgt = rh.GaussianTargetDensity2d(rh.ParameterVector(TGT_MEAN), TGT_COV)
+    sur = rh.GaussianTargetDensity2d(rh.ParameterVector(surMean), surCov)
+    traj, acc, lpc, lpf, order = [], [], [], [], []
+    for c in range(nChains):
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        b = rh.MLDABuilder()
+        b.explicitTarget = tgt
+        b.surrogateTargets = [sur]
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, 1.)
+        b.subChainLengths = [J]
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.array([-8., -7.])), nSteps, inj, True)
+        traj.append(t); acc.append(a)
+        lpf.append(logpost_along(tgt, rh.ParameterVector, t))
+        lpc.append(logpost_along(sur, rh.ParameterVector, t))
+        order.append(''.join(inj.log))
+    m1, P1, c1 = gauss2d_level_arrays(TGT_MEAN, TGT_COV)
+    m0, P0, c0 = gauss2d_level_arrays(surMean, surCov)
+    meta = dict(model='gauss', dim=2, levels=2, J=J, eq='exact', rng_order=order,
+                note='example_mcmc_2d_twoLevel.py:10-40')
+    save("mlda_gauss2d", meta, dict(
+        prop_L=lower_proposal('iid', 1., 2),
+        L0_g_mean=m0, L0_g_prec=P0, L0_g_logconst=c0,
+        L1_g_mean=m1, L1_g_prec=P1, L1_g_logconst=c1,
+        theta0=np.tile([-8., -7.], (nChains, 1)), z=z, u_c=u_c, u_f=u_f,
+        traj=traj, accepted=acc, logpost_L0=lpc, logpost_L1=lpf))
+
+
+# --------------------------------------------------------------------------
+# linear model (C3)
+# --------------------------------------------------------------------------
+
+def linear_problem():
+    G_f = np.array([[1.4, -0.2], [-0.6, 0.7]])
+    b_f = np.zeros(2)
+    G_c = G_f + np.array([[-0.6, -0.2], [0.4, 1.1]])
+    b_c = np.array([0.5, -0.9])
+    truth = np.array([1.5, 0.5])
+    rng = Generator(Philox(2222))
+    data = np.array([G_f @ truth + b_f + np.sqrt(0.3) * rng.standard_normal(2) for _ in range(5)])
+    priorMean = truth + np.array([-0.2, 0.4])
+    return dict(G_f=G_f, b_f=b_f, G_c=G_c, b_c=b_c, data=data, noiseVar=np.sqrt(0.3)**2,
+                priorMean=priorMean, priorVar=5.0, propVar=0.5)
+
+
+def linear_models(p):
+    data = rh.Data(p['data'])
+    noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(2, p['noiseVar']))
+    prior = rh.Gaussian(rh.ParameterVector(p['priorMean']), rh.IIDCovarianceMatrix(2, p['priorVar']))
+    likC = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_c'], p['b_c'])), noise)
+    likF = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_f'], p['b_f'])), noise)
+    return likC, likF, prior
+
+
+def linear_level_arrays(p, lvl, prefix):
+    return {
+        prefix + 'data': p['data'],
+        prefix + 'noise_prec': diag_precision(p['noiseVar'], 2),
+        prefix + 'prior_mean': p['priorMean'],
+        prefix + 'prior_prec': diag_precision(p['priorVar'], 2),
+        prefix + 'G': p['G_' + lvl], prefix + 'b': p['b_' + lvl]}
+
+
+def case_linear(twoLevel):
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = linear_problem()
+    nChains, nSteps, J = 3, 300, (5 if twoLevel else 1)
+    rng = Generator(Philox(404 + J))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2,
+                             zero_at=[(0, 4, None), (1, 8, 1)] if twoLevel else [(0, 4, 0)])
+    traj, acc, lpc, lpf = [], [], [], []
+    for c in range(nChains):
+        likC, likF, prior = linear_models(p)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        if twoLevel:
+            b = rh.MLDABuilder()
+            b.bayesModel = rh.BayesianRegressionModelHierarchy(
+                rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+            b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+            b.subChainLengths = [J]
+        else:
+            b = rh.MRWBuilder()
+            b.bayesModel = rh.BayesianRegressionModel(likF, prior)
+            b.proposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.zeros(2)), nSteps, inj, twoLevel)
+        traj.append(t); acc.append(a)
+        lpf.append(logpost_along(UnnormalisedPosterior(likF, prior), rh.ParameterVector, t))
+        lpc.append(logpost_along(UnnormalisedPosterior(likC, prior), rh.ParameterVector, t))
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], 2),
+                  theta0=np.zeros((nChains, 2)), z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc)
+    if twoLevel:
+        arrays.update(linear_level_arrays(p, 'c', 'L0_'))
+        arrays.update(linear_level_arrays(p, 'f', 'L1_'))
+        arrays.update(logpost_L0=lpc, logpost_L1=lpf)
+    else:
+        arrays.update(linear_level_arrays(p, 'f', 'L0_'))
+        arrays.update(logpost_L0=lpf)
+    meta = dict(model='linear', dim=2, levels=2 if twoLevel else 1, J=J, eq='exact',
+                note='C3 example_inference_linearModel_twoLevel.py:33-74,128-129,173')
+    save("mlda_linear" if twoLevel else "mrw_linear", meta, arrays)
+
+
+# --------------------------------------------------------------------------
+# Lotka-Volterra (C4 / C5)
+# --------------------------------------------------------------------------
+
+def lv_problem(Nc=64, Nf=512, T=10., nData=10, seed=1112):
+    rng = Generator(Philox(seed))
+    design = rng.uniform(0.5, 1.5, (nData, 2))
+    truth = np.log(np.array([0.4, 0.6]))
+    cfg = dict(T=T, alpha=0.8, gamma=0.4, nData=nData, dataDim=2)
+    sol = rh.RK4LotkaVolterraSolver(design, dict(cfg, rk4Steps=Nf))
+    sol.interpolate(rh.LotkaVolterraParameter.from_coefficient(truth))
+    sol.invoke()
+    data = sol.evaluation + np.sqrt(0.04) * rng.standard_normal((nData, 2))
+    return dict(design=design, truth=truth, cfg=cfg, data=data, Nc=Nc, Nf=Nf,
+                noiseVar=0.04, priorVar=1.4, priorMean=np.zeros(2))
+
+
+def lv_models(p):
+    data = rh.Data(p['data'])
+    noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(2, p['noiseVar']))
+    prior = rh.Gaussian(rh.LotkaVolterraParameter.from_coefficient(p['priorMean']),
+                        rh.IIDCovarianceMatrix(2, p['priorVar']))
+    solC = rh.RK4LotkaVolterraSolver(p['design'], dict(p['cfg'], rk4Steps=p['Nc']))
+    solF = rh.RK4LotkaVolterraSolver(p['design'], dict(p['cfg'], rk4Steps=p['Nf']))
+    likC = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(solC), noise)
+    likF = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(solF), noise)
+    return likC, likF, prior
+
+
+def lv_level_arrays(p, N, prefix):
+    return {
+        prefix + 'data': p['data'],
+        prefix + 'noise_prec': diag_precision(p['noiseVar'], 2),
+        prefix + 'prior_mean': p['priorMean'],
+        prefix + 'prior_prec': diag_precision(p['priorVar'], 2),
+        prefix + 'design': p['design'],
+        prefix + 'lv': np.array([p['cfg']['alpha'], p['cfg']['gamma'], p['cfg']['T'], float(N)])}
+
+
+def case_lv(name, twoLevel, p, propVar, nChains, nSteps, J, seed, theta0, zero_at=(), zscale=None, note=''):
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=zero_at)
+    if zscale is not None:
+        for (c, n, j, s) in zscale:
+            z[c, n, j, :] *= s
+    traj, acc, lpc, lpf = [], [], [], []
+    for c in range(nChains):
+        likC, likF, prior = lv_models(p)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        if twoLevel:
+            b = rh.MLDABuilder()
+            b.bayesModel = rh.BayesianRegressionModelHierarchy(
+                rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+            b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, propVar)
+            b.subChainLengths = [J]
+        else:
+            b = rh.MRWBuilder()
+            b.bayesModel = rh.BayesianRegressionModel(likF, prior)
+            b.proposalCovariance = rh.IIDCovarianceMatrix(2, propVar)
+        mcmc = rh.quiet(b.build_method)
+        init = rh.LotkaVolterraParameter.from_coefficient(theta0[c].copy())
+        t, a = rh.run_reference_chain(mcmc, init, nSteps, inj, twoLevel)
+        traj.append(t); acc.append(a)
+        lpf.append(logpost_along(UnnormalisedPosterior(likF, prior), rh.LotkaVolterraParameter, t))
+        if twoLevel:
+            lpc.append(logpost_along(UnnormalisedPosterior(likC, prior), rh.LotkaVolterraParameter, t))
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('iid', propVar, 2),
+                  theta0=theta0, z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc)
+    if twoLevel:
+        arrays.update(lv_level_arrays(p, p['Nc'], 'L0_'))
+        arrays.update(lv_level_arrays(p, p['Nf'], 'L1_'))
+        arrays.update(logpost_L0=lpc, logpost_L1=lpf)
+    else:
+        arrays.update(lv_level_arrays(p, p['Nf'], 'L0_'))
+        arrays.update(logpost_L0=lpf)
+    meta = dict(model='lv', dim=2, levels=2 if twoLevel else 1, J=J, eq='exact', note=note)
+    save(name, meta, arrays)
+
+
+def cases_lv():
+    p = lv_problem()
+    rng = Generator(Philox(7))
+    theta0 = p['truth'] + 0.05 * rng.standard_normal((3, 2))
+    case_lv("mrw_lv", False, p, 0.15, 3, 120, 1, 505, theta0, zero_at=[(0, 6, 0)],
+            note='C4 example_inference_lotkaVolterra_singleLevel.py:29-59,82-83 with RK4 N=512')
+    case_lv("mlda_lv", True, p, 0.1, 3, 120, 3, 606, theta0,
+            zero_at=[(0, 4, None), (1, 9, 1)],
+            note='C5 example_inference_lotkaVolterra_twoLevel.py:29-44,95-106 with RK4 Nc=64 Nf=512, J=3')
+    # non-finite forward outputs: tiny RK4 step count + huge proposals, and a start in the NaN region
+    pe = lv_problem(Nc=8, Nf=16)
+    theta0e = np.array([[-7., 2.8], p['truth'], [3.0, 4.0]])
+    case_lv("mlda_lv_nonfinite", True, pe, 0.1, 3, 60, 2, 707, theta0e,
+            zscale=[(1, 3, 0, 40.0), (1, 10, 1, 60.0), (0, 2, 0, 25.0), (2, 5, 0, 30.0)],
+            note='edge: RK4 overflow -> +inf forward output -> logL=-inf; -inf/-inf -> NaN ratio accepts '
+                 '(mrw.py:54-57); SURVEY section 7')
+
+
+# --------------------------------------------------------------------------
+# post-processing pins: IAT, Welford, dense covariance
+# --------------------------------------------------------------------------
+
+def case_postprocessing():
+    from yagremcmc.postprocessing.autocorrelation import (
+        integrated_autocorrelation, estimate_autocorrelation_function_1d)
+    from yagremcmc.statistics.estimation import WelfordAccumulator
+    rng = Generator(Philox(808))
+    seqs, iat_max, iat_mean, acfs = [], [], [], []
+    for rho, n in [(0.0, 500), (0.5, 1000), (0.9, 2000), (0.97, 3000), (0.8, 777)]:
+        e = rng.standard_normal((n, 2))
+        x = np.zeros((n, 2))
+        for i in range(1, n):
+            x[i] = np.array([rho, 0.5 * rho]) * x[i - 1] + e[i]
+        seqs.append(x)
+        iat_max.append(integrated_autocorrelation(x, 'max'))
+        iat_mean.append(integrated_autocorrelation(x, 'mean'))
+        acfs.append(estimate_autocorrelation_function_1d(x[:, 0])[:64])
+    arrays = {f'seq{i}': s for i, s in enumerate(seqs)}
+    arrays.update({f'acf{i}': a for i, a in enumerate(acfs)})
+    arrays['iat_max'] = np.array(iat_max)
+    arrays['iat_mean'] = np.array(iat_mean)
+    # Welford (estimation.py:36-53)
+    w = WelfordAccumulator()
+    xs = rng.standard_normal((1000, 3)) * np.array([1., 3., 0.1]) + np.array([5., -2., 0.])
+    for x in xs:
+        w.update(x)
+    arrays['welford_x'] = xs
+    arrays['welford_mean'] = w.mean()
+    arrays['welford_var'] = w.marginal_variance()
+    arrays['welford_cond'] = w.condition_number()
+    # dense covariance operator (covariance.py:69-94)
+    C = np.array([[2.0, 0.6, -0.3], [0.6, 1.0, 0.2], [-0.3, 0.2, 0.5]])
+    dc = rh.DenseCovarianceMatrix(C)
+    v = rng.standard_normal((16, 3))
+    arrays['dense_C'] = C
+    arrays['dense_v'] = v
+    arrays['dense_chol_apply'] = np.array([dc.apply_chol_factor(x) for x in v])
+    arrays['dense_inv_apply'] = np.array([dc.apply_inverse(x) for x in v])
+    arrays['dense_norm2'] = np.array([dc.induced_norm_squared(x) for x in v])
+    save("postprocessing", dict(note='autocorrelation.py:5-140, estimation.py:36-53, covariance.py:69-94'), arrays)
+
+
+if __name__ == "__main__":
+    only = set(sys.argv[1:])
+
+    def want(k):
+        return not only or k in only
+    if want('gauss'):
+        case_gauss1d()
+        case_gauss2d("mrw_gauss2d_iid", 'iid', 1.0, 201)
+        case_gauss2d("mrw_gauss2d_diag", 'diag', [1.5, 0.4], 202)
+        case_gauss2d("mrw_gauss2d_dense", 'dense', [[1.2, -0.3], [-0.3, 0.5]], 203)
+        case_mlda_gauss2d()
+    if want('linear'):
+        case_linear(False)
+        case_linear(True)
+    if want('post'):
+        case_postprocessing()
+    if want('lv'):
+        cases_lv()

@@ -1,0 +1,26 @@
+"""Loads tests/golden/*.npz (written by oracle/make_golden.py from the reference)."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CHAIN_CASES = ["mrw_gauss1d", "mrw_gauss2d_iid", "mrw_gauss2d_diag", "mrw_gauss2d_dense",
+               "mlda_gauss2d", "mrw_linear", "mlda_linear", "mrw_lv", "mlda_lv", "mlda_lv_nonfinite"]
+
+
+def load(name):
+    f = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(f["meta"]))
+    arrays = {k: f[k] for k in f.files if k != "meta"}
+    return meta, arrays
+
+
+def rel_err(a, b):
+    """Relative error that treats equal infinities / NaNs as matching."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    with np.errstate(all='ignore'):
+        e = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    return np.where(same, 0.0, e)

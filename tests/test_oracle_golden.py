@@ -1,0 +1,93 @@
+"""CPU: pins the C oracle (oracle/yagre_oracle.c) against the fixtures the
+unmodified reference produced under injected noise (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import cport
+from golden_io import load, rel_err, CHAIN_CASES
+
+LOGPOST_RTOL = 1e-10     # north_star: 1e-10 relative on log-posterior
+
+
+@pytest.mark.parametrize("name", CHAIN_CASES)
+def test_chain_trajectory_matches_reference(name):
+    meta, a = load(name)
+    pb = cport.Problem(meta, a)
+    out = cport.run_injected(pb, a["theta0"], a["z"], a["u_c"], a["u_f"])
+    # identical accept decisions
+    assert np.array_equal(out["accepted"], a["accepted"]), name
+    # trajectories: proposals are s + L z in both, so states agree to rounding
+    assert rel_err(out["traj"], a["traj"]).max() <= 1e-13, name
+    assert rel_err(out["logpost_L0"], a["logpost_L0"]).max() <= LOGPOST_RTOL, name
+    if meta["levels"] == 2:
+        assert rel_err(out["logpost_L1"], a["logpost_L1"]).max() <= LOGPOST_RTOL, name
+    if "welford_mean" in a:     # FullDiagnostics: Welford of the pre-transition state
+        np.testing.assert_allclose(out["welford_mean"], a["welford_mean"], rtol=1e-12)
+        np.testing.assert_allclose(out["welford_var"], a["welford_var"], rtol=1e-12)
+
+
+def test_rng_call_order_of_reference_is_what_the_restatement_assumes():
+    """(N u)*J then U only if the sub-chain moved."""
+    meta, a = load("mlda_gauss2d")
+    J = meta["J"]
+    for c, order in enumerate(meta["rng_order"]):
+        # strip per fine step
+        i = 0
+        for n in range(a["u_f"].shape[1]):
+            moved = False
+            for j in range(J):
+                assert order[i] == 'N'; i += 1
+                if i < len(order) and order[i] == 'u':
+                    i += 1
+                else:
+                    assert np.all(a["z"][c, n, j] == 0.0)     # equality skip: no uniform drawn
+            if i < len(order) and order[i] == 'U':
+                i += 1
+                moved = True
+            same = np.array_equal(a["traj"][c, n + 1], a["traj"][c, n])
+            assert moved or same
+        assert i == len(order)
+
+
+def test_nonfinite_policy():
+    meta, a = load("mlda_lv_nonfinite")
+    # chain 0 starts where RK4(16) overflows: logpost = -inf on both levels
+    assert np.isneginf(a["logpost_L1"][0, 0]) and np.isneginf(a["logpost_L0"][0, 0])
+    pb = cport.Problem(meta, a)
+    assert np.isneginf(cport.logpost(pb, 1, a["theta0"][0]))
+    F = cport.forward(pb, 1, a["theta0"][0])
+    assert np.all(np.isposinf(F) | np.isfinite(F)) and np.isposinf(F).any()
+
+
+def test_iat_welford_dense_match_reference():
+    _, a = load("postprocessing")
+    for i in range(5):
+        s = a[f"seq{i}"]
+        assert cport.iat(s, 'max') == int(a["iat_max"][i])
+        assert cport.iat(s, 'mean') == int(a["iat_mean"][i])
+        np.testing.assert_allclose(cport.acf(s[:, 0])[:64], a[f"acf{i}"], rtol=0, atol=1e-12)
+    m, v = cport.welford(a["welford_x"])
+    np.testing.assert_allclose(m, a["welford_mean"], rtol=1e-13)
+    np.testing.assert_allclose(v, a["welford_var"], rtol=1e-13)
+    L = cport.cholesky(a["dense_C"])
+    for x, y1, y2, n2 in zip(a["dense_v"], a["dense_chol_apply"], a["dense_inv_apply"], a["dense_norm2"]):
+        np.testing.assert_allclose(cport.chol_apply(L, x), y1, rtol=1e-13, atol=1e-15)
+        inv = cport.chol_solve(L, x)
+        np.testing.assert_allclose(inv, y2, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(np.dot(x, inv), n2, rtol=1e-12)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    assert cport.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert cport.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert cport.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_streams_statistics():
+    z = np.array([cport.philox_normals(7, c, s, 0, 2) for c in range(50) for s in range(100)])
+    u = np.array([cport.philox_uniform(7, c, s, 0xFFFF) for c in range(50) for s in range(100)])
+    assert abs(z.mean()) < 0.05 and abs(z.var() - 1) < 0.05
+    assert abs(u.mean() - 0.5) < 0.02 and 0 <= u.min() and u.max() < 1
