@@ -1,0 +1,466 @@
+// abi.cu -- the extern "C" surface of libyagre_b200.so (include/yagre_b200.h).
+// Plain pointers and sizes only; no torch types, no exceptions across the boundary.
+#include "ensemble.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+int yg_pooled_impl(const double *w_mean, const double *w_m2, const unsigned long long *n_accept, int d, int64_t nc,
+                   int64_t welford_n, double *partials, int n_part, double *out_dev, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void yg_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr int POOL_PARTS = 64;
+
+int check_handle(const yg_ensemble *e, bool need_problem, bool need_state)
+{
+    if (!e) {
+        yg_set_error("null ensemble handle");
+        return YG_ERR_INVALID;
+    }
+    if (need_problem && !e->problem_set) {
+        yg_set_error("yg_set_problem has not been called");
+        return YG_ERR_STATE;
+    }
+    if (need_state && !e->state_set) {
+        yg_set_error("yg_set_state / yg_load_state has not been called");
+        return YG_ERR_STATE;
+    }
+    return YG_OK;
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t n)
+{
+    YG_CUDA_CHECK(cudaMalloc((void **)p, sizeof(T) * std::max<size_t>(n, 1)));
+    YG_CUDA_CHECK(cudaMemset(*p, 0, sizeof(T) * std::max<size_t>(n, 1)));
+    return YG_OK;
+}
+
+void copy_mat(double *dst, const double *src, int rows, int cols)
+{
+    if (src) memcpy(dst, src, sizeof(double) * rows * cols);
+}
+
+RunArgs make_args(yg_ensemble *e)
+{
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.problem = e->d_problem;
+    a.problem_bytes = (uint32_t)e->h_problem.size();
+    a.thin = 1;
+    a.n_chains = e->cfg.n_chains;
+    a.chain_offset = e->cfg.chain_offset;
+    a.seed = e->cfg.seed;
+    a.step0 = e->step_index;
+    a.welford_n0 = e->welford_n;
+    a.theta = e->theta;
+    a.logpost = e->logpost;
+    a.n_accept = e->n_accept;
+    a.w_mean = e->w_mean;
+    a.w_m2 = e->w_m2;
+    a.am_mean = e->am_mean;
+    a.am_m2 = e->am_m2;
+    a.prop_L = e->prop_L;
+    a.adaptive = e->cfg.adaptive;
+    a.am_refresh = std::max(1, e->cfg.am_refresh);
+    a.am_idle = e->cfg.am_idle_steps;
+    a.am_collect = e->cfg.am_collection_steps;
+    a.am_eps = e->cfg.am_eps;
+    a.am_scale = e->cfg.am_scale > 0.0 ? e->cfg.am_scale : 2.4 * 2.4 / (double)e->cfg.dim;
+    a.counters = e->counters;
+    return a;
+}
+
+__global__ void broadcast_L_kernel(const DevProblemHeader *pb, double *prop_L, int64_t n)
+{
+    const int d = pb->dim;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x)
+        for (int k = 0; k < d * d; k++) prop_L[(int64_t)k * n + g] = pb->prop_L[k];
+}
+
+}  // namespace
+
+extern "C" const char *yg_last_error(void) { return g_err; }
+extern "C" uint32_t yg_abi_version(void) { return YG_ABI_VERSION; }
+
+extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
+{
+    if (!cfg || !out) {
+        yg_set_error("yg_create: null argument");
+        return YG_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (cfg->abi_version != YG_ABI_VERSION) {
+        yg_set_error("abi_version %u != library %u", cfg->abi_version, YG_ABI_VERSION);
+        return YG_ERR_ABI;
+    }
+    if (cfg->n_chains < 1 || cfg->dim < 1 || cfg->dim > YG_MAX_DIM) {
+        yg_set_error("n_chains=%lld dim=%d out of range (dim 1..%d)", (long long)cfg->n_chains, cfg->dim, YG_MAX_DIM);
+        return YG_ERR_INVALID;
+    }
+    if (cfg->n_levels != 1 && cfg->n_levels != 2) {
+        yg_set_error("n_levels=%d: only MRW (1) and two-level delayed acceptance (2) exist on the device",
+                     cfg->n_levels);
+        return YG_ERR_UNSUPPORTED;
+    }
+    if (cfg->n_levels == 2 && cfg->sub_chain_length < 1) {
+        yg_set_error("sub_chain_length must be >= 1");
+        return YG_ERR_INVALID;
+    }
+    if (cfg->model != YG_MODEL_GAUSS && cfg->model != YG_MODEL_LINEAR && cfg->model != YG_MODEL_LV_RK4) {
+        yg_set_error("unknown model %d", cfg->model);
+        return YG_ERR_UNSUPPORTED;
+    }
+    if (cfg->model == YG_MODEL_LV_RK4 && cfg->dim != 2) {
+        yg_set_error("the Lotka-Volterra model has two parameters (dim=%d)", cfg->dim);
+        return YG_ERR_INVALID;
+    }
+    if (cfg->adaptive && (cfg->n_levels != 1 || cfg->model == YG_MODEL_LV_RK4 || cfg->dim < 2)) {
+        yg_set_error("adaptive Metropolis: single level, dim >= 2, Gaussian/linear models only");
+        return YG_ERR_UNSUPPORTED;   // dim == 1: chain/adaptive.py:41-43 refuses scalar chains too
+    }
+    if (cfg->eq_mode == YG_EQ_ISCLOSE && cfg->dim != 1) {
+        yg_set_error("isclose equality is the ScalarParameter rule (dim must be 1)");
+        return YG_ERR_INVALID;
+    }
+    int ndev = 0;
+    YG_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        yg_set_error("device %d not present (%d visible)", cfg->device, ndev);
+        return YG_ERR_INVALID;
+    }
+    YG_CUDA_CHECK(cudaSetDevice(cfg->device));
+    yg_ensemble *e = new (std::nothrow) yg_ensemble();
+    if (!e) {
+        yg_set_error("out of host memory");
+        return YG_ERR_INVALID;
+    }
+    e->cfg = *cfg;
+    YG_CUDA_CHECK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    const size_t n = (size_t)cfg->n_chains, d = (size_t)cfg->dim;
+    int rc = YG_OK;
+    if ((rc = dev_alloc(&e->theta, d * n)) || (rc = dev_alloc(&e->logpost, 2 * n)) ||
+        (rc = dev_alloc(&e->w_mean, d * n)) || (rc = dev_alloc(&e->w_m2, d * d * n)) ||
+        (rc = dev_alloc(&e->n_accept, n)) || (rc = dev_alloc(&e->counters, 8)) ||
+        (rc = dev_alloc(&e->pool_partials, (size_t)POOL_PARTS * (size_t)yg_pooled_len(cfg->dim)))) {
+        yg_destroy(e);
+        return rc;
+    }
+    if (cfg->adaptive) {
+        if ((rc = dev_alloc(&e->am_mean, d * n)) || (rc = dev_alloc(&e->am_m2, d * d * n)) ||
+            (rc = dev_alloc(&e->prop_L, d * d * n))) {
+            yg_destroy(e);
+            return rc;
+        }
+    }
+    *out = e;
+    return YG_OK;
+}
+
+extern "C" int yg_destroy(yg_ensemble *e)
+{
+    if (!e) return YG_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaFree(e->d_problem);
+    cudaFree(e->theta);
+    cudaFree(e->logpost);
+    cudaFree(e->w_mean);
+    cudaFree(e->w_m2);
+    cudaFree(e->am_mean);
+    cudaFree(e->am_m2);
+    cudaFree(e->prop_L);
+    cudaFree(e->n_accept);
+    cudaFree(e->counters);
+    cudaFree(e->pool_partials);
+    delete e;
+    return YG_OK;
+}
+
+extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
+{
+    int rc = check_handle(e, false, false);
+    if (rc) return rc;
+    if (!pb || !pb->prop_L) {
+        yg_set_error("yg_set_problem: problem / prop_L is null");
+        return YG_ERR_INVALID;
+    }
+    const int d = e->cfg.dim, nl = e->cfg.n_levels, model = e->cfg.model;
+    // tail: per level data + design
+    size_t tail_len = 0;
+    for (int l = 0; l < nl; l++) {
+        const yg_level &L = pb->level[l];
+        if (model == YG_MODEL_GAUSS) {
+            if (!L.g_mean || !L.g_prec) {
+                yg_set_error("level %d: Gaussian target needs g_mean and g_prec", l);
+                return YG_ERR_INVALID;
+            }
+            continue;
+        }
+        if (!L.data || !L.noise_prec || !L.prior_mean || !L.prior_prec || L.n_data < 1 || L.data_dim < 1 ||
+            L.data_dim > YG_MAX_DATA_DIM) {
+            yg_set_error("level %d: regression level needs data[n_data>=1, data_dim<=%d], noise_prec, prior", l,
+                         YG_MAX_DATA_DIM);
+            return YG_ERR_INVALID;
+        }
+        if (model == YG_MODEL_LINEAR && (!L.G || !L.b)) {
+            yg_set_error("level %d: linear model needs G and b", l);
+            return YG_ERR_INVALID;
+        }
+        if (model == YG_MODEL_LV_RK4) {
+            if (!L.design || L.data_dim != 2 || L.rk4_steps < 1 || !(L.T > 0.0)) {
+                yg_set_error("level %d: LV model needs design[n_data,2], data_dim=2, rk4_steps>=1, T>0", l);
+                return YG_ERR_INVALID;
+            }
+        }
+        tail_len += (size_t)L.n_data * L.data_dim;
+        if (model == YG_MODEL_LV_RK4) tail_len += (size_t)L.n_data * 2;
+    }
+    tail_len = (tail_len + 1) & ~size_t(1);        // keep the blob a multiple of 16 bytes
+    std::vector<char> blob(sizeof(DevProblemHeader) + sizeof(double) * tail_len, 0);
+    DevProblemHeader *h = reinterpret_cast<DevProblemHeader *>(blob.data());
+    double *tail = reinterpret_cast<double *>(blob.data() + sizeof(DevProblemHeader));
+    h->model = model;
+    h->dim = d;
+    h->n_levels = nl;
+    h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
+    h->eq_mode = e->cfg.eq_mode;
+    h->tail_len = (int32_t)tail_len;
+    copy_mat(h->prop_L, pb->prop_L, d, d);
+    for (int i = 0; i < d; i++)
+        for (int j = i + 1; j < d; j++)
+            if (h->prop_L[i * d + j] != 0.0) {
+                yg_set_error("prop_L must be lower triangular");
+                return YG_ERR_INVALID;
+            }
+    size_t off = 0;
+    for (int l = 0; l < nl; l++) {
+        const yg_level &L = pb->level[l];
+        DevLevel &D = h->lvl[l];
+        if (model == YG_MODEL_GAUSS) {
+            copy_mat(D.g_mean, L.g_mean, 1, d);
+            copy_mat(D.g_prec, L.g_prec, d, d);
+            D.g_logconst = L.g_logconst;
+            continue;
+        }
+        D.n_data = L.n_data;
+        D.data_dim = L.data_dim;
+        copy_mat(D.noise_prec, L.noise_prec, L.data_dim, L.data_dim);
+        copy_mat(D.prior_mean, L.prior_mean, 1, d);
+        copy_mat(D.prior_prec, L.prior_prec, d, d);
+        D.data_off = (int32_t)off;
+        memcpy(tail + off, L.data, sizeof(double) * L.n_data * L.data_dim);
+        off += (size_t)L.n_data * L.data_dim;
+        if (model == YG_MODEL_LINEAR) {
+            copy_mat(D.G, L.G, L.data_dim, d);
+            copy_mat(D.b, L.b, 1, L.data_dim);
+        } else {
+            D.alpha = L.alpha;
+            D.gamma = L.gamma;
+            D.T = L.T;
+            D.rk4_steps = L.rk4_steps;
+            D.design_off = (int32_t)off;
+            memcpy(tail + off, L.design, sizeof(double) * L.n_data * 2);
+            off += (size_t)L.n_data * 2;
+        }
+    }
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    if (e->d_problem) cudaFree(e->d_problem);
+    e->d_problem = nullptr;
+    YG_CUDA_CHECK(cudaMalloc((void **)&e->d_problem, blob.size()));
+    YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    e->h_problem.swap(blob);
+    e->problem_set = true;
+    return YG_OK;
+}
+
+extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stream)
+{
+    int rc = check_handle(e, true, false);
+    if (rc) return rc;
+    if (!theta0_dev) {
+        yg_set_error("theta0_dev is null");
+        return YG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)e->cfg.n_chains, d = (size_t)e->cfg.dim;
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    YG_CUDA_CHECK(cudaMemcpyAsync(e->theta, theta0_dev, sizeof(double) * d * n, cudaMemcpyDeviceToDevice, st));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->w_mean, 0, sizeof(double) * d * n, st));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->w_m2, 0, sizeof(double) * d * d * n, st));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->n_accept, 0, sizeof(unsigned long long) * n, st));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->counters, 0, sizeof(unsigned long long) * 8, st));
+    if (e->cfg.adaptive) {
+        YG_CUDA_CHECK(cudaMemsetAsync(e->am_mean, 0, sizeof(double) * d * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->am_m2, 0, sizeof(double) * d * d * n, st));
+        broadcast_L_kernel<<<(int)std::min<size_t>((n + 127) / 128, 2048), 128, 0, st>>>(e->d_problem, e->prop_L,
+                                                                                      (int64_t)n);
+        YG_CUDA_CHECK(cudaGetLastError());
+    }
+    for (int l = 0; l < e->cfg.n_levels; l++) {
+        rc = yg_launch_logpost(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st);
+        if (rc) return rc;
+    }
+    e->step_index = 0;
+    e->welford_n = 0;
+    e->state_set = true;
+    return YG_OK;
+}
+
+extern "C" int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin, const yg_outputs *out, const yg_noise *noise,
+                      void *stream)
+{
+    int rc = check_handle(e, true, true);
+    if (rc) return rc;
+    if (n_steps < 0 || thin < 1) {
+        yg_set_error("n_steps=%lld thin=%d invalid", (long long)n_steps, thin);
+        return YG_ERR_INVALID;
+    }
+    if (n_steps == 0) return YG_OK;
+    RunArgs a = make_args(e);
+    a.n_steps = n_steps;
+    a.thin = thin;
+    if (out) {
+        a.samples = out->samples_dev;
+        a.accepted = out->accepted_dev;
+        a.lp_out = out->logpost_dev;
+        if ((a.samples || a.lp_out) && n_steps % thin) {
+            yg_set_error("n_steps (%lld) must be a multiple of thin (%d) when samples are stored",
+                         (long long)n_steps, thin);
+            return YG_ERR_INVALID;
+        }
+    }
+    if (noise && noise->mode != YG_NOISE_PHILOX) {
+        if (noise->mode != YG_NOISE_INJECT && noise->mode != YG_NOISE_RECORD) {
+            yg_set_error("unknown noise mode %d", noise->mode);
+            return YG_ERR_INVALID;
+        }
+        if (!noise->z_dev || !noise->u_f_dev || (e->cfg.n_levels == 2 && !noise->u_c_dev)) {
+            yg_set_error("noise mode %d needs z_dev, u_f_dev%s", noise->mode,
+                         e->cfg.n_levels == 2 ? " and u_c_dev" : "");
+            return YG_ERR_INVALID;
+        }
+        a.noise_mode = noise->mode;
+        a.z = noise->z_dev;
+        a.u_c = noise->u_c_dev;
+        a.u_f = noise->u_f_dev;
+    }
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    rc = (e->cfg.model == YG_MODEL_LV_RK4) ? yg_launch_lv(e, a, false, (cudaStream_t)stream)
+                                           : yg_launch_generic(e, a, false, (cudaStream_t)stream);
+    if (rc) return rc;
+    e->step_index += n_steps;
+    e->welford_n += n_steps;
+    return YG_OK;
+}
+
+extern "C" int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream)
+{
+    int rc = check_handle(e, true, true);
+    if (rc) return rc;
+    if (!dst) return YG_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)e->cfg.n_chains, d = (size_t)e->cfg.dim, nl = (size_t)e->cfg.n_levels;
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    if (dst->theta_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->theta_dev, e->theta, 8 * d * n, k, st));
+    if (dst->logpost_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->logpost_dev, e->logpost, 8 * nl * n, k, st));
+    if (dst->n_accept_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->n_accept_dev, e->n_accept, 8 * n, k, st));
+    if (dst->w_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->w_mean_dev, e->w_mean, 8 * d * n, k, st));
+    if (dst->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->w_m2_dev, e->w_m2, 8 * d * d * n, k, st));
+    if (dst->prop_L_dev) {
+        if (!e->cfg.adaptive) {
+            yg_set_error("prop_L_dev is per-chain state of adaptive ensembles only");
+            return YG_ERR_INVALID;
+        }
+        YG_CUDA_CHECK(cudaMemcpyAsync(dst->prop_L_dev, e->prop_L, 8 * d * d * n, k, st));
+    }
+    return YG_OK;
+}
+
+extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n, void *stream)
+{
+    int rc = check_handle(e, true, false);
+    if (rc) return rc;
+    if (!src || !src->theta_dev || !src->logpost_dev) {
+        yg_set_error("yg_load_state needs at least theta_dev and logpost_dev");
+        return YG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)e->cfg.n_chains, d = (size_t)e->cfg.dim, nl = (size_t)e->cfg.n_levels;
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    YG_CUDA_CHECK(cudaMemcpyAsync(e->theta, src->theta_dev, 8 * d * n, k, st));
+    YG_CUDA_CHECK(cudaMemcpyAsync(e->logpost, src->logpost_dev, 8 * nl * n, k, st));
+    if (src->n_accept_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->n_accept, src->n_accept_dev, 8 * n, k, st));
+    if (src->w_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_mean, src->w_mean_dev, 8 * d * n, k, st));
+    if (src->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_m2, src->w_m2_dev, 8 * d * d * n, k, st));
+    if (src->prop_L_dev && e->cfg.adaptive)
+        YG_CUDA_CHECK(cudaMemcpyAsync(e->prop_L, src->prop_L_dev, 8 * d * d * n, k, st));
+    e->step_index = step_index;
+    e->welford_n = welford_n;
+    e->state_set = true;
+    return YG_OK;
+}
+
+extern "C" int yg_get_counters(yg_ensemble *e, int64_t *out_host, void *stream)
+{
+    int rc = check_handle(e, false, false);
+    if (rc) return rc;
+    if (!out_host) return YG_ERR_INVALID;
+    unsigned long long c[8];
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    YG_CUDA_CHECK(cudaMemcpyAsync(c, e->counters, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    YG_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    out_host[0] = e->step_index;
+    out_host[1] = (int64_t)c[0];
+    out_host[2] = (int64_t)c[1];
+    out_host[3] = (int64_t)c[2];
+    out_host[4] = (int64_t)c[3];
+    out_host[5] = e->welford_n;
+    return YG_OK;
+}
+
+extern "C" int yg_logpost(yg_ensemble *e, int32_t level, const double *theta_dev, int64_t n, double *out_dev,
+                          void *stream)
+{
+    int rc = check_handle(e, true, false);
+    if (rc) return rc;
+    if (level < 0 || level >= e->cfg.n_levels || !theta_dev || !out_dev || n < 1) {
+        yg_set_error("yg_logpost: invalid arguments");
+        return YG_ERR_INVALID;
+    }
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    return yg_launch_logpost(e, level, theta_dev, n, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int yg_pooled_stats(yg_ensemble *e, double *out_dev, void *stream)
+{
+    int rc = check_handle(e, true, true);
+    if (rc) return rc;
+    if (!out_dev) return YG_ERR_INVALID;
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    return yg_pooled_impl(e->w_mean, e->w_m2, e->n_accept, e->cfg.dim, e->cfg.n_chains, e->welford_n,
+                          e->pool_partials, POOL_PARTS, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int yg_last_launch(yg_ensemble *e, int32_t *grid, int32_t *block, int32_t *smem_bytes, int64_t *launches)
+{
+    if (!e) return YG_ERR_INVALID;
+    if (grid) *grid = e->last_grid;
+    if (block) *block = e->last_block;
+    if (smem_bytes) *smem_bytes = e->last_smem;
+    if (launches) *launches = e->launches;
+    return YG_OK;
+}

@@ -1,0 +1,55 @@
+// ensemble.h -- host-side handle and the argument block passed to the step kernels.
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+struct RunArgs {
+    const DevProblemHeader *problem;
+    uint32_t problem_bytes;
+    int32_t thin;
+    int64_t n_chains, chain_offset;
+    uint64_t seed;
+    int64_t step0, n_steps, welford_n0;
+    // per-chain state, SoA, chain index fastest
+    double *theta;                  // [d, n]
+    double *logpost;                // [2, n]
+    unsigned long long *n_accept;   // [n]
+    double *w_mean;                 // [d, n]
+    double *w_m2;                   // [d*d, n]
+    // adaptive Metropolis (generic kernel only)
+    double *am_mean;                // [d, n]
+    double *am_m2;                  // [d*d, n]
+    double *prop_L;                 // [d*d, n]
+    int32_t adaptive, am_refresh;
+    int64_t am_idle, am_collect;
+    double am_eps, am_scale;
+    // outputs
+    double *samples;                // [n_steps/thin, d, n]
+    uint8_t *accepted;              // [n_steps, n]
+    double *lp_out;                 // [n_steps/thin, n_levels, n]
+    // noise
+    int32_t noise_mode, _pad;
+    double *z, *u_c, *u_f;
+    // [0] transitions [1] accepted [2] level-0 evals [3] level-1 evals
+    unsigned long long *counters;
+};
+
+struct yg_ensemble {
+    yg_config cfg;
+    int sm_count = 0;
+    bool problem_set = false, state_set = false;
+    std::vector<char> h_problem;
+    DevProblemHeader *d_problem = nullptr;
+    double *theta = nullptr, *logpost = nullptr, *w_mean = nullptr, *w_m2 = nullptr;
+    double *am_mean = nullptr, *am_m2 = nullptr, *prop_L = nullptr;
+    unsigned long long *n_accept = nullptr, *counters = nullptr;
+    double *pool_partials = nullptr;   // [POOL_PARTS][yg_pooled_len(d)] scratch of yg_pooled_stats
+    int64_t step_index = 0, welford_n = 0;
+    int last_grid = 0, last_block = 0, last_smem = 0;
+    int64_t launches = 0;
+};
+
+// kernels' host launchers (lv_kernel.cu, generic_kernel.cu, diag_kernels.cu)
+int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool init_only, cudaStream_t st);
+int yg_launch_generic(yg_ensemble *e, const RunArgs &a, bool init_only, cudaStream_t st);
+int yg_launch_logpost(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st);

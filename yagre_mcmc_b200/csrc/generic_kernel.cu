@@ -1,0 +1,472 @@
+// generic_kernel.cu -- one chain per thread, everything in registers: the
+// Metropolis-Hastings step for cheap targets (explicit Gaussian densities and the
+// linear model G.theta + b), single level or two-level delayed acceptance, with
+// optional per-chain adaptive Metropolis.  Also the log-posterior evaluator used
+// by yg_set_state / yg_logpost for every model (LV included).
+//
+// Reference semantics restated (rkutri/yagre-mcmc):
+//   Gaussian targets     test/testSetup.py:15-44
+//   linear forward       exampleSetup.py:42-52 (A @ theta + b)
+//   likelihood / prior   statistics/likelihood.py:33-39,74-84, statistics/gaussian.py:19-24
+//   proposal             statistics/gaussian.py:61-66, statistics/covariance.py:51-52,84-86
+//   MRW / MLDA ratios    chain/method/mrw.py:51-57, chain/method/mlda.py:146-154
+//   step loop            chain/metropolisHastings.py:55-120
+//   adaptive interface   chain/adaptive.py:37-64 (update() before each proposal);
+//                        recurrence: DESIGN.md "Adaptive Metropolis" (the reference's
+//                        own AM, chain/method/deprecated/am.py, does not run)
+//
+// These targets cost a few hundred FP64 instructions per step, dominated by the
+// transcendental sequences of Box-Muller and exp; the kernel is bound by FP64
+// issue with the sample write-back (8 d bytes per chain-step, coalesced SoA) as
+// the secondary bound.
+#include "ensemble.h"
+#include "lv_model.cuh"
+#include <math_constants.h>
+
+namespace {
+
+// numpy-ordered streaming sum of q_0..q_{n-1} produced by `next(i)` (np.sum, n <= 128 exact)
+template <typename F>
+YG_DEVFN double np_stream_sum(int n, F next)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res += next(i);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = next(k);
+    const int n8 = n - (n % 8);
+    for (int i = 8; i < n8; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] += next(i + k);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (int i = n8; i < n; i++) res += next(i);
+    return res;
+}
+
+// log-posterior of one parameter vector at `lvl` (chain/target.py:19-22)
+template <int D, int DD>
+YG_DEVFN double logpost_any(const DevProblemHeader *pb, int lvl, const double (&t)[D])
+{
+    const DevLevel &Lv = pb->lvl[lvl];
+    const int d = pb->dim;
+    double x[D];
+    if (pb->model == YG_MODEL_GAUSS) {
+#pragma unroll
+        for (int i = 0; i < D; i++) x[i] = (i < d) ? t[i] - Lv.g_mean[i] : 0.0;
+        return -0.5 * quad_form<D>(Lv.g_prec, d, x, d) + Lv.g_logconst;
+    }
+    const double *tail = dev_tail(pb);
+    const double *data = tail + Lv.data_off;
+    const int nD = Lv.n_data, dd = Lv.data_dim;
+    double sum;
+    if (pb->model == YG_MODEL_LINEAR) {
+        double F[DD];
+#pragma unroll
+        for (int k = 0; k < DD; k++) {
+            double acc = 0.0;
+            if (k < dd) {
+#pragma unroll
+                for (int j = 0; j < D; j++)
+                    if (j < d) acc = (j == 0) ? Lv.G[k * d] * t[0] : fma(Lv.G[k * d + j], t[j], acc);
+                acc += Lv.b[k];
+            }
+            F[k] = acc;
+        }
+        sum = np_stream_sum(nD, [&](int n) {
+            double r[DD];
+#pragma unroll
+            for (int k = 0; k < DD; k++) r[k] = (k < dd) ? F[k] - data[n * dd + k] : 0.0;
+            return quad_form<DD>(Lv.noise_prec, dd, r, dd);
+        });
+    } else {   // YG_MODEL_LV_RK4 (thread-per-parameter evaluation; the hot path is lv_kernel.cu)
+        const double *design = tail + Lv.design_off;
+        const LvRates rates = lv_rates(Lv.alpha, Lv.gamma, Lv.T, Lv.rk4_steps, exp(t[0]), exp(t[D > 1 ? 1 : 0]));
+        sum = np_stream_sum(nD, [&](int n) {
+            double X = design[2 * n], Y = design[2 * n + 1];
+            lv_integrate(rates, Lv.rk4_steps, X, Y);
+            const double r[2] = {X - data[2 * n], Y - data[2 * n + 1]};
+            return quad_form<2>(Lv.noise_prec, 2, r, 2);
+        });
+    }
+    const double logL = -0.5 * sum;
+#pragma unroll
+    for (int i = 0; i < D; i++) x[i] = (i < d) ? t[i] - Lv.prior_mean[i] : 0.0;
+    return logL + (-0.5 * quad_form<D>(Lv.prior_prec, d, x, d));
+}
+
+__device__ void stage_blob(unsigned char *smem, const DevProblemHeader *g, uint32_t bytes)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(g);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+template <int D, int DD>
+__global__ void logpost_kernel(const DevProblemHeader *gpb, uint32_t bytes, int lvl, const double *theta,
+                               int64_t n, double *out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_blob(smem_raw, gpb, bytes);
+    const DevProblemHeader *pb = reinterpret_cast<const DevProblemHeader *>(smem_raw);
+    const int d = pb->dim;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+        double t[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) t[i] = (i < d) ? theta[i * n + g] : 0.0;
+        out[g] = logpost_any<D, DD>(pb, lvl, t);
+    }
+}
+
+// In-register Cholesky of the d x d leading block; returns false if not positive definite.
+template <int D>
+YG_DEVFN bool cholesky_lower(const double (&C)[D][D], double (&L)[D][D], int d)
+{
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        if (j < d) {
+            double s = C[j][j];
+#pragma unroll
+            for (int k = 0; k < D; k++)
+                if (k < j) s -= L[j][k] * L[j][k];
+            if (!(s > 0.0)) return false;
+            const double ljj = sqrt(s);
+            L[j][j] = ljj;
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                if (i > j && i < d) {
+                    double v = C[i][j];
+#pragma unroll
+                    for (int k = 0; k < D; k++)
+                        if (k < j) v -= L[i][k] * L[j][k];
+                    L[i][j] = v / ljj;
+                }
+                if (i < j) L[i][j] = 0.0;
+            }
+        }
+    }
+    return true;
+}
+
+template <int D, int DD, bool TWO_LEVEL>
+__global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_blob(smem_raw, a.problem, a.problem_bytes);
+    const DevProblemHeader *pb = reinterpret_cast<const DevProblemHeader *>(smem_raw);
+    const int d = pb->dim;
+    const int J = TWO_LEVEL ? pb->J : 1;
+    const int n_lvl = TWO_LEVEL ? 2 : 1;
+    const int64_t N = a.n_chains;
+    const bool isclose_eq = pb->eq_mode == YG_EQ_ISCLOSE;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < N; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t gid = (uint64_t)(a.chain_offset + g);
+        double th[D], wm[D], w2[D][D], L[D][D];
+        double am_m[D], am_2[D][D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            th[i] = (i < d) ? a.theta[i * N + g] : 0.0;
+            wm[i] = (i < d) ? a.w_mean[i * N + g] : 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                w2[i][j] = (i < d && j < d) ? a.w_m2[(i * d + j) * N + g] : 0.0;
+                L[i][j] = (i < d && j < d) ? (a.adaptive ? a.prop_L[(i * d + j) * N + g] : pb->prop_L[i * d + j]) : 0.0;
+                am_2[i][j] = (a.adaptive && i < d && j < d) ? a.am_m2[(i * d + j) * N + g] : 0.0;
+            }
+            am_m[i] = (a.adaptive && i < d) ? a.am_mean[i * N + g] : 0.0;
+        }
+        double lp0 = a.logpost[g], lp1 = TWO_LEVEL ? a.logpost[N + g] : 0.0;
+        unsigned long long nacc = a.n_accept[g];
+
+        auto equal = [&](const double (&p)[D], const double (&s)[D]) {
+            if (isclose_eq) return isclose_rule(p[0], s[0]);
+            bool eq = true;
+#pragma unroll
+            for (int i = 0; i < D; i++)
+                if (i < d) eq = eq && (p[i] == s[i]);
+            return eq;
+        };
+        // p = s + L z, unfused, exact zeros of L skipped (covariance.py:51-52,84-86)
+        auto propose = [&](const double (&s)[D], int64_t n, int j, uint64_t step, double (&p)[D]) {
+            double z[D];
+            if (a.noise_mode == YG_NOISE_INJECT) {
+#pragma unroll
+                for (int i = 0; i < D; i++) z[i] = (i < d) ? a.z[((n * J + j) * d + i) * N + g] : 0.0;
+            } else {
+#pragma unroll
+                for (int b = 0; b < (D + 1) / 2; b++) {
+                    if (2 * b < d) {
+                        double z0, z1;
+                        philox_normal_pair(a.seed, gid, step, (uint32_t)j, (uint32_t)b, z0, z1);
+                        z[2 * b] = z0;
+                        if (2 * b + 1 < D) z[2 * b + 1] = z1;
+                    }
+                }
+                if (a.noise_mode == YG_NOISE_RECORD) {
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                        if (i < d) a.z[((n * J + j) * d + i) * N + g] = z[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double acc = 0.0;
+                bool first = true;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    if (k <= i && i < d) {
+                        const double l = L[i][k];
+                        if (l != 0.0 || k == i) {
+                            const double t = __dmul_rn(l, z[k]);
+                            acc = first ? t : __dadd_rn(acc, t);
+                            first = false;
+                        }
+                    }
+                }
+                p[i] = (i < d) ? __dadd_rn(s[i], acc) : 0.0;
+            }
+        };
+
+        for (int64_t n = 0; n < a.n_steps; n++) {
+            const uint64_t step = (uint64_t)(a.step0 + n);
+            // ---- diagnostics Welford of the pre-transition state (diagnostics.py:91-94) ----
+            {
+                const double wn = (double)(a.welford_n0 + n + 1);
+                double dl[D], e[D];
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    dl[i] = th[i] - wm[i];
+                    wm[i] += dl[i] / wn;
+                    e[i] = th[i] - wm[i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; i++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) w2[i][j] += dl[i] * e[j];
+            }
+            // ---- adaptive Metropolis: update() before the proposal (adaptive.py:55-60) ----
+            if (a.adaptive) {
+                const int64_t t_idx = a.step0 + n;
+                if (t_idx >= a.am_idle) {
+                    const int64_t n_am = t_idx - a.am_idle + 1;
+                    double dl[D], e[D];
+#pragma unroll
+                    for (int i = 0; i < D; i++) {
+                        dl[i] = th[i] - am_m[i];
+                        am_m[i] += dl[i] / (double)n_am;
+                        e[i] = th[i] - am_m[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+#pragma unroll
+                        for (int j = 0; j < D; j++) am_2[i][j] += dl[i] * e[j];
+                    if (n_am >= a.am_collect && n_am >= 2 && ((n_am - a.am_collect) % a.am_refresh) == 0) {
+                        double Cm[D][D], Ln[D][D];
+#pragma unroll
+                        for (int i = 0; i < D; i++)
+#pragma unroll
+                            for (int j = 0; j < D; j++) {
+                                // symmetrised sample covariance, C = s (Cov + eps I)
+                                const double cov = 0.5 * (am_2[i][j] + am_2[j][i]) / (double)(n_am - 1);
+                                Cm[i][j] = a.am_scale * (cov + ((i == j) ? a.am_eps : 0.0));
+                                Ln[i][j] = 0.0;
+                            }
+                        if (cholesky_lower<D>(Cm, Ln, d)) {
+#pragma unroll
+                            for (int i = 0; i < D; i++)
+#pragma unroll
+                                for (int j = 0; j < D; j++) L[i][j] = Ln[i][j];
+                        }
+                    }
+                }
+            }
+            bool accepted = false;
+            if (!TWO_LEVEL) {
+                double p[D];
+                propose(th, n, 0, step, p);
+                if (!equal(p, th)) {                                    // metropolisHastings.py:60-61
+                    const double lpp = logpost_any<D, DD>(pb, 0, p);
+                    cnt_ev0++;
+                    double u;
+                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
+                    else {
+                        u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                        if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
+                    }
+                    if (accept_rule(lpp - lp0, u)) {
+#pragma unroll
+                        for (int i = 0; i < D; i++) th[i] = p[i];
+                        lp0 = lpp;
+                        accepted = true;
+                    }
+                }
+            } else {
+                double s[D], p[D];
+#pragma unroll
+                for (int i = 0; i < D; i++) s[i] = th[i];
+                double lps = lp0;
+                for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
+                    propose(s, n, j, step, p);
+                    if (equal(p, s)) continue;
+                    const double lpp = logpost_any<D, DD>(pb, 0, p);
+                    cnt_ev0++;
+                    double u;
+                    const int64_t ui = (n * J + j) * N + g;
+                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
+                    else {
+                        u = philox_uniform(a.seed, gid, step, (uint32_t)j);
+                        if (a.noise_mode == YG_NOISE_RECORD) a.u_c[ui] = u;
+                    }
+                    if (accept_rule(lpp - lps, u)) {
+#pragma unroll
+                        for (int i = 0; i < D; i++) s[i] = p[i];
+                        lps = lpp;
+                    }
+                }
+                if (!equal(s, th)) {
+                    const double lpf_s = logpost_any<D, DD>(pb, 1, s);
+                    cnt_ev1++;
+                    double u;
+                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
+                    else {
+                        u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                        if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
+                    }
+                    const double delta = lpf_s + lp0 - lps - lp1;      // mlda.py:148-152, this order
+                    if (accept_rule(delta, u)) {
+#pragma unroll
+                        for (int i = 0; i < D; i++) th[i] = s[i];
+                        lp0 = lps;
+                        lp1 = lpf_s;
+                        accepted = true;
+                    }
+                }
+            }
+            if (accepted) { nacc++; cnt_acc++; }
+            cnt_tr++;
+            if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+            if ((n + 1) % a.thin == 0) {
+                const int64_t o = (n + 1) / a.thin - 1;
+                if (a.samples) {
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                        if (i < d) a.samples[(o * d + i) * N + g] = th[i];
+                }
+                if (a.lp_out) {
+                    a.lp_out[(o * n_lvl) * N + g] = lp0;
+                    if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + g] = lp1;
+                }
+            }
+        }
+        // ---- store chain state ---------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            if (i < d) {
+                a.theta[i * N + g] = th[i];
+                a.w_mean[i * N + g] = wm[i];
+                if (a.adaptive) a.am_mean[i * N + g] = am_m[i];
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    if (j < d) {
+                        a.w_m2[(i * d + j) * N + g] = w2[i][j];
+                        if (a.adaptive) {
+                            a.am_m2[(i * d + j) * N + g] = am_2[i][j];
+                            a.prop_L[(i * d + j) * N + g] = L[i][j];
+                        }
+                    }
+                }
+            }
+        }
+        a.logpost[g] = lp0;
+        if (TWO_LEVEL) a.logpost[N + g] = lp1;
+        a.n_accept[g] = nacc;
+    }
+    // ---- counters: warp-shuffle reduction, one atomic per warp ------------------------------
+    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
+    }
+}
+
+int cap_of(int n)
+{
+    return n <= 2 ? 2 : (n <= 4 ? 4 : 8);
+}
+
+template <int D, int DD>
+int launch_generic_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
+{
+    const int threads = 128;
+    const int64_t want = (a.n_chains + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
+    const size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
+    auto kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true> : generic_mh_kernel<D, DD, false>;
+    YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->last_grid = grid;
+    e->last_block = threads;
+    e->last_smem = (int)smem;
+    e->launches += 1;
+    return YG_OK;
+}
+
+template <int D, int DD>
+int launch_logpost_t(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st)
+{
+    const int threads = 128;
+    const int64_t want = (n + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
+    const size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
+    auto kern = logpost_kernel<D, DD>;
+    YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(e->d_problem, (uint32_t)e->h_problem.size(), level, theta, n, out);
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->launches += 1;
+    return YG_OK;
+}
+
+#define YG_DISPATCH(FN, ...)                                                  \
+    switch (cd * 16 + cdd) {                                                   \
+    case 2 * 16 + 2: return FN<2, 2>(__VA_ARGS__);                             \
+    case 2 * 16 + 4: return FN<2, 4>(__VA_ARGS__);                             \
+    case 2 * 16 + 8: return FN<2, 8>(__VA_ARGS__);                             \
+    case 4 * 16 + 2: return FN<4, 2>(__VA_ARGS__);                             \
+    case 4 * 16 + 4: return FN<4, 4>(__VA_ARGS__);                             \
+    case 4 * 16 + 8: return FN<4, 8>(__VA_ARGS__);                             \
+    case 8 * 16 + 2: return FN<8, 2>(__VA_ARGS__);                             \
+    case 8 * 16 + 4: return FN<8, 4>(__VA_ARGS__);                             \
+    case 8 * 16 + 8: return FN<8, 8>(__VA_ARGS__);                             \
+    default: break;                                                            \
+    }
+
+}  // namespace
+
+int yg_launch_generic(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
+{
+    const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
+    const int cd = cap_of(hp->dim);
+    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim)));
+    YG_DISPATCH(launch_generic_t, e, a, st)
+    yg_set_error("unsupported dimensions d=%d data_dim=%d", hp->dim, hp->lvl[0].data_dim);
+    return YG_ERR_UNSUPPORTED;
+}
+
+int yg_launch_logpost(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st)
+{
+    const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
+    const int cd = cap_of(hp->dim);
+    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim)));
+    YG_DISPATCH(launch_logpost_t, e, level, theta, n, out, st)
+    yg_set_error("unsupported dimensions d=%d data_dim=%d", hp->dim, hp->lvl[0].data_dim);
+    return YG_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,382 @@
+// lv_kernel.cu -- the headline hot path: Metropolis-Hastings over an ensemble of
+// independent chains on the Lotka-Volterra (RK4) posterior, single level (MRW)
+// or two-level delayed acceptance (MLDA with one surrogate).
+//
+// Reference semantics restated (rkutri/yagre-mcmc):
+//   step loop            chain/metropolisHastings.py:103-120
+//   proposal             chain/method/mrw.py:27-38 -> statistics/gaussian.py:61-66
+//   equality skip        chain/metropolisHastings.py:60-61, parameter/vector.py:37-45
+//   likelihood           statistics/likelihood.py:33-39,74-84, statistics/covariance.py:19-22
+//   prior / posterior    statistics/gaussian.py:19-24, chain/target.py:19-22
+//   coarse sub-chain     chain/method/mlda.py:100-110
+//   fine screen          chain/method/mlda.py:146-154 (this summation order)
+//   Welford diagnostics  chain/diagnostics.py:91-94, statistics/estimation.py:36-53
+//
+// B200 mapping (DESIGN.md "LV kernel"):
+//   * persistent CTAs, grid = SMs x blocks_per_sm, every CTA resident; a CTA owns
+//     a contiguous range of chains and walks it in chunks of <= CMAX chains, each
+//     chunk running all n_steps with no inter-CTA communication;
+//   * the unit of FP64 work is one ODE integration = (chain, design point): after
+//     the owners' phase has proposed, the CTA spreads `active chains x n_data`
+//     integrations over ALL its threads, so a chain whose coarse sub-chain did not
+//     move (no fine evaluation, mlda.py / metropolisHastings.py:60-61) costs
+//     nothing in the fine phase -- block-level compaction instead of lane masks;
+//   * ODE state and the four scaled rate constants live in registers, chain state
+//     lives in shared memory between phases so the integration loop stays small
+//     enough for 1024 resident threads/SM; several CTAs per SM sit in different
+//     phases, which hides the owners' phases and the tails of the item loops;
+//   * the problem blob (design points, observations, precisions) is staged once
+//     per CTA into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier).
+#include "ensemble.h"
+#include "lv_model.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int LV_D = 2;
+
+struct SmemLayout {
+    // doubles per chain slot
+    enum { TH0, TH1, LP0, LP1, S0, S1, LPS, P0, P1, BETA, DELTA, WM0, WM1, W00, W01, W10, W11, NDBL };
+};
+
+YG_DEVFN uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One TMA bulk copy global -> shared, completion on an mbarrier (UBLKCP in SASS).
+YG_DEVFN void tma_stage_blob(void *dst, const void *src, uint32_t bytes, uint64_t *mbar)
+{
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst)),
+            "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+            : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar))
+            : "memory");
+    }
+}
+
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(256, 4) lv_mh_kernel(const RunArgs a, const int cmax)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- shared memory carve-up ------------------------------------------------
+    DevProblemHeader *pb = reinterpret_cast<DevProblemHeader *>(smem_raw);
+    size_t off = (a.problem_bytes + 15u) & ~size_t(15);
+    double *chain = reinterpret_cast<double *>(smem_raw + off);            // [NDBL][cmax]
+    off += sizeof(double) * SmemLayout::NDBL * cmax;
+    const int nd_max = max(a.problem->lvl[0].n_data, TWO_LEVEL ? a.problem->lvl[1].n_data : 0);
+    double *q = reinterpret_cast<double *>(smem_raw + off);                // [n_data][cmax]
+    off += sizeof(double) * (size_t)nd_max * cmax;
+    unsigned long long *nacc = reinterpret_cast<unsigned long long *>(smem_raw + off);   // [cmax]
+    off += sizeof(unsigned long long) * cmax;
+    int *list0 = reinterpret_cast<int *>(smem_raw + off);                  // [2][cmax]
+    off += sizeof(int) * 2 * cmax;
+    unsigned char *evald = smem_raw + off;                                 // [cmax]
+    off += (cmax + 15) & ~15;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + off);
+    int *nact = reinterpret_cast<int *>(mbar + 1);                         // [2]
+    unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [4]
+
+    tma_stage_blob(pb, a.problem, (uint32_t)((a.problem_bytes + 15u) & ~15u), mbar);
+    if (tid < 4) blk_cnt[tid] = 0ull;
+    if (tid < 2) nact[tid] = 0;
+
+    const double *tail = dev_tail(pb);
+    const int J = TWO_LEVEL ? pb->J : 1;
+    const int n_lvl = TWO_LEVEL ? 2 : 1;
+    const double L00 = pb->prop_L[0], L10 = pb->prop_L[LV_D], L11 = pb->prop_L[LV_D + 1];
+
+#define CH(field, c) chain[(SmemLayout::field) * cmax + (c)]
+
+    // chains of this CTA: even split of [0, n_chains) over the grid
+    const int64_t cta_lo = (a.n_chains * (int64_t)blockIdx.x) / gridDim.x;
+    const int64_t cta_hi = (a.n_chains * (int64_t)(blockIdx.x + 1)) / gridDim.x;
+    const int64_t N = a.n_chains;
+
+    // ---- one phase of forward evaluations over the compacted list ---------------
+    auto eval_phase = [&](int lvl, int cur) {
+        const DevLevel &Lv = pb->lvl[lvl];
+        const int na = nact[cur];
+        const int nD = Lv.n_data;
+        const int nItems = na * nD;
+        const int *lst = list0 + cur * cmax;
+        const double *design = tail + Lv.design_off;
+        const double *data = tail + Lv.data_off;
+        const double P00 = Lv.noise_prec[0], P01 = Lv.noise_prec[1], P10 = Lv.noise_prec[2], P11 = Lv.noise_prec[3];
+        if (tid == 0) {
+            nact[cur ^ 1] = 0;
+            blk_cnt[2 + lvl] += (unsigned long long)na;
+        }
+        for (int it = tid; it < nItems; it += nthr) {
+            const int ai = it % na, n = it / na;
+            const int c = lst[ai];
+            const LvRates r = lv_rates(Lv.alpha, Lv.gamma, Lv.T, Lv.rk4_steps, CH(BETA, c), CH(DELTA, c));
+            double x = design[2 * n], y = design[2 * n + 1];
+            lv_integrate(r, Lv.rk4_steps, x, y);
+            const double r0 = x - data[2 * n], r1 = y - data[2 * n + 1];
+            // r' P r with P applied first; exact zeros skipped (diagonal noise, inf-safe)
+            double t0 = P00 * r0;
+            if (P01 != 0.0) t0 = fma(P01, r1, t0);
+            double t1 = (P10 != 0.0) ? P10 * r0 : 0.0;
+            t1 = (P10 != 0.0) ? fma(P11, r1, t1) : P11 * r1;
+            q[n * cmax + c] = fma(r1, t1, r0 * t0);
+        }
+    };
+
+    auto log_prior = [&](int lvl, double t0, double t1) {
+        const DevLevel &Lv = pb->lvl[lvl];
+        const double x[2] = {t0 - Lv.prior_mean[0], t1 - Lv.prior_mean[1]};
+        return -0.5 * quad_form<2>(Lv.prior_prec, LV_D, x, 2);
+    };
+    auto log_post_from_q = [&](int lvl, int c, double t0, double t1) {
+        const double logL = -0.5 * np_pairwise_sum(q + c, pb->lvl[lvl].n_data, cmax);
+        return logL + log_prior(lvl, t0, t1);
+    };
+
+    // noise access: injected arrays are indexed by (step, sub-step), never by call count
+    auto uniform_c = [&](int64_t n, int j, int64_t g, uint64_t gid, uint64_t step) {
+        const int64_t i = (n * J + j) * N + g;
+        if (a.noise_mode == YG_NOISE_INJECT) return a.u_c[i];
+        const double u = philox_uniform(a.seed, gid, step, (uint32_t)j);
+        if (a.noise_mode == YG_NOISE_RECORD) a.u_c[i] = u;
+        return u;
+    };
+    auto uniform_f = [&](int64_t n, int64_t g, uint64_t gid, uint64_t step) {
+        const int64_t i = n * N + g;
+        if (a.noise_mode == YG_NOISE_INJECT) return a.u_f[i];
+        const double u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+        if (a.noise_mode == YG_NOISE_RECORD) a.u_f[i] = u;
+        return u;
+    };
+
+    int cur = 0;
+    for (int64_t cb = cta_lo; cb < cta_hi; cb += cmax) {
+        const int C = (int)min((int64_t)cmax, cta_hi - cb);
+        __syncthreads();
+        // ---- load chunk state ---------------------------------------------------
+        for (int c = tid; c < C; c += nthr) {
+            const int64_t g = cb + c;
+            CH(TH0, c) = a.theta[g];
+            CH(TH1, c) = a.theta[N + g];
+            CH(LP0, c) = a.logpost[g];
+            CH(LP1, c) = TWO_LEVEL ? a.logpost[N + g] : 0.0;
+            CH(WM0, c) = a.w_mean[g];
+            CH(WM1, c) = a.w_mean[N + g];
+            CH(W00, c) = a.w_m2[g];
+            CH(W01, c) = a.w_m2[N + g];
+            CH(W10, c) = a.w_m2[2 * N + g];
+            CH(W11, c) = a.w_m2[3 * N + g];
+            nacc[c] = a.n_accept[g];
+        }
+        unsigned long long my_acc = 0ull;
+
+        for (int64_t n = 0; n < a.n_steps; n++) {
+            const uint64_t step = (uint64_t)(a.step0 + n);
+            const double wn = (double)(a.welford_n0 + n + 1);
+            // Phases j = 0..J-1: decide sub-step j-1, propose sub-step j, evaluate level 0.
+            // Two level only, phase j = J: decide sub-step J-1, evaluate level 1 where the
+            // sub-chain moved.  Then the commit below decides the transition.
+            const int n_phases = TWO_LEVEL ? J + 1 : 1;
+            for (int j = 0; j < n_phases; j++) {
+                // =============== owners' phase ===================================
+                for (int c = tid; c < C; c += nthr) {
+                    const int64_t g = cb + c;
+                    const uint64_t gid = (uint64_t)(a.chain_offset + g);
+                    double s0, s1, lps;
+                    if (j == 0) {
+                        // FullDiagnostics: Welford of the pre-transition state
+                        // (diagnostics.py:91-94, estimation.py:36-53)
+                        const double t0 = CH(TH0, c), t1 = CH(TH1, c);
+                        const double d0 = t0 - CH(WM0, c), d1 = t1 - CH(WM1, c);
+                        const double m0 = CH(WM0, c) + d0 / wn, m1 = CH(WM1, c) + d1 / wn;
+                        const double e0 = t0 - m0, e1 = t1 - m1;
+                        CH(WM0, c) = m0; CH(WM1, c) = m1;
+                        CH(W00, c) += d0 * e0; CH(W01, c) += d0 * e1;
+                        CH(W10, c) += d1 * e0; CH(W11, c) += d1 * e1;
+                        s0 = t0; s1 = t1; lps = CH(LP0, c);
+                    } else {
+                        // coarse decision of sub-step j-1 (mrw.py:51-57)
+                        s0 = CH(S0, c); s1 = CH(S1, c); lps = CH(LPS, c);
+                        if (evald[c]) {
+                            const double p0 = CH(P0, c), p1 = CH(P1, c);
+                            const double lpp = log_post_from_q(0, c, p0, p1);
+                            if (accept_rule(lpp - lps, uniform_c(n, j - 1, g, gid, step))) {
+                                s0 = p0; s1 = p1; lps = lpp;
+                            }
+                        }
+                    }
+                    CH(S0, c) = s0; CH(S1, c) = s1; CH(LPS, c) = lps;
+                    if (j < J) {
+                        // propose sub-step j: p = s + L z  (gaussian.py:61-66), unfused like numpy
+                        double z0, z1;
+                        const int64_t zi = ((n * J + j) * LV_D) * N + g;
+                        if (a.noise_mode == YG_NOISE_INJECT) {
+                            z0 = a.z[zi]; z1 = a.z[zi + N];
+                        } else {
+                            philox_normal_pair(a.seed, gid, step, (uint32_t)j, 0u, z0, z1);
+                            if (a.noise_mode == YG_NOISE_RECORD) { a.z[zi] = z0; a.z[zi + N] = z1; }
+                        }
+                        const double p0 = __dadd_rn(s0, __dmul_rn(L00, z0));
+                        const double lz1 = (L10 != 0.0) ? __dadd_rn(__dmul_rn(L10, z0), __dmul_rn(L11, z1))
+                                                        : __dmul_rn(L11, z1);
+                        const double p1 = __dadd_rn(s1, lz1);
+                        const bool eq = (p0 == s0) && (p1 == s1);   // vector.py:37-45
+                        evald[c] = !eq;
+                        CH(P0, c) = p0; CH(P1, c) = p1;
+                        if (!eq) {
+                            CH(BETA, c) = exp(p0);     // LotkaVolterraParameter.evaluate, testSetup.py:57-58
+                            CH(DELTA, c) = exp(p1);
+                            list0[cur * cmax + atomicAdd(&nact[cur], 1)] = c;
+                        }
+                    } else {
+                        // sub-chain finished: s is the MLDA proposal (mlda.py:106-110); a chain whose
+                        // sub-chain did not move is rejected without a fine evaluation and without
+                        // consuming a uniform (metropolisHastings.py:60-61)
+                        const bool moved = !((s0 == CH(TH0, c)) && (s1 == CH(TH1, c)));
+                        evald[c] = moved;
+                        if (moved) {
+                            CH(BETA, c) = exp(s0);
+                            CH(DELTA, c) = exp(s1);
+                            list0[cur * cmax + atomicAdd(&nact[cur], 1)] = c;
+                        }
+                    }
+                }
+                __syncthreads();
+                // =============== forward evaluations =============================
+                eval_phase((TWO_LEVEL && j == J) ? 1 : 0, cur);
+                __syncthreads();
+                cur ^= 1;
+            }
+            // =============== commit the transition ===============================
+            for (int c = tid; c < C; c += nthr) {
+                const int64_t g = cb + c;
+                const uint64_t gid = (uint64_t)(a.chain_offset + g);
+                bool accepted = false;
+                if (evald[c]) {
+                    if (TWO_LEVEL) {
+                        const double s0 = CH(S0, c), s1 = CH(S1, c);
+                        const double lpf_s = log_post_from_q(1, c, s0, s1);
+                        // mlda.py:148-152: pi_f(p) + pi_c(s) - pi_c(p) - pi_f(s), left to right
+                        const double delta = lpf_s + CH(LP0, c) - CH(LPS, c) - CH(LP1, c);
+                        if (accept_rule(delta, uniform_f(n, g, gid, step))) {
+                            CH(TH0, c) = s0; CH(TH1, c) = s1;
+                            CH(LP0, c) = CH(LPS, c); CH(LP1, c) = lpf_s;
+                            accepted = true;
+                        }
+                    } else {
+                        const double p0 = CH(P0, c), p1 = CH(P1, c);
+                        const double lpp = log_post_from_q(0, c, p0, p1);
+                        if (accept_rule(lpp - CH(LP0, c), uniform_f(n, g, gid, step))) {
+                            CH(TH0, c) = p0; CH(TH1, c) = p1; CH(LP0, c) = lpp;
+                            accepted = true;
+                        }
+                    }
+                }
+                if (accepted) { nacc[c] += 1ull; my_acc += 1ull; }
+                if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+                if ((n + 1) % a.thin == 0) {
+                    const int64_t o = (n + 1) / a.thin - 1;
+                    if (a.samples) {
+                        a.samples[(o * LV_D) * N + g] = CH(TH0, c);
+                        a.samples[(o * LV_D + 1) * N + g] = CH(TH1, c);
+                    }
+                    if (a.lp_out) {
+                        a.lp_out[(o * n_lvl) * N + g] = CH(LP0, c);
+                        if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + g] = CH(LP1, c);
+                    }
+                }
+            }
+            // the next owners' phase touches only the owner's own slots and list `cur`,
+            // whose counter was zeroed during the last evaluation phase: no barrier needed
+        }
+
+        // ---- store chunk state --------------------------------------------------
+        for (int c = tid; c < C; c += nthr) {
+            const int64_t g = cb + c;
+            a.theta[g] = CH(TH0, c);
+            a.theta[N + g] = CH(TH1, c);
+            a.logpost[g] = CH(LP0, c);
+            if (TWO_LEVEL) a.logpost[N + g] = CH(LP1, c);
+            a.w_mean[g] = CH(WM0, c);
+            a.w_mean[N + g] = CH(WM1, c);
+            a.w_m2[g] = CH(W00, c);
+            a.w_m2[N + g] = CH(W01, c);
+            a.w_m2[2 * N + g] = CH(W10, c);
+            a.w_m2[3 * N + g] = CH(W11, c);
+            a.n_accept[g] = nacc[c];
+        }
+        if (my_acc) atomicAdd(&blk_cnt[1], my_acc);
+        if (tid == 0) blk_cnt[0] += (unsigned long long)C * (unsigned long long)a.n_steps;
+    }
+    __syncthreads();
+    if (tid < 4 && blk_cnt[tid]) atomicAdd(&a.counters[tid], blk_cnt[tid]);
+#undef CH
+}
+
+size_t lv_smem_bytes(const yg_ensemble *e, int cmax, int nd_max)
+{
+    size_t off = (e->h_problem.size() + 15u) & ~size_t(15);
+    off += sizeof(double) * SmemLayout::NDBL * cmax;
+    off += sizeof(double) * (size_t)nd_max * cmax;
+    off += sizeof(unsigned long long) * cmax;
+    off += sizeof(int) * 2 * cmax;
+    off += (cmax + 15) & ~15;
+    off += 8 + 8 + 32;
+    return (off + 15) & ~size_t(15);
+}
+
+}  // namespace
+
+int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
+{
+    const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
+    const bool two = e->cfg.n_levels == 2;
+    const int nd_max = std::max(hp->lvl[0].n_data, two ? hp->lvl[1].n_data : 0);
+    int threads = e->cfg.threads_per_block > 0 ? e->cfg.threads_per_block : 256;
+    int bps = e->cfg.blocks_per_sm > 0 ? e->cfg.blocks_per_sm : 4;
+    if (threads % 32 || threads > 256) {
+        yg_set_error("threads_per_block must be a multiple of 32 and <= 256 (got %d)", threads);
+        return YG_ERR_INVALID;
+    }
+    int64_t grid64 = std::min<int64_t>((int64_t)e->sm_count * bps, a.n_chains);
+    int grid = (int)std::max<int64_t>(grid64, 1);
+    // chains per chunk: the CTA's share, capped so that shared memory fits bps CTAs per SM
+    int64_t share = (a.n_chains + grid - 1) / grid;
+    const size_t budget = (size_t)(220 * 1024) / bps;
+    const size_t fixed = lv_smem_bytes(e, 0, nd_max);
+    const size_t per_chain = sizeof(double) * (SmemLayout::NDBL + nd_max) + 8 + 8 + 1;
+    int64_t cap = fixed < budget ? (int64_t)((budget - fixed) / per_chain) : 0;
+    if (cap < 1) {
+        yg_set_error("problem blob too large for shared memory (%zu bytes)", fixed);
+        return YG_ERR_UNSUPPORTED;
+    }
+    const int cmax = (int)std::max<int64_t>(1, std::min<int64_t>(share, std::min<int64_t>(cap, 1024)));
+    const size_t smem = lv_smem_bytes(e, cmax, nd_max);
+    auto kern = two ? lv_mh_kernel<true> : lv_mh_kernel<false>;
+    YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a, cmax);
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->last_grid = grid;
+    e->last_block = threads;
+    e->last_smem = (int)smem;
+    e->launches += 1;
+    return YG_OK;
+}

@@ -1,0 +1,292 @@
+"""Host-side handle over libyagre_b200: an ensemble of independent chains on one GPU.
+
+PyTorch is plumbing only (device memory, streams); every computation happens in
+the hand-written sm_100a kernels behind the C-ABI.  Layout on the device is
+struct-of-arrays with the chain index fastest (theta[d, n], samples[n_out, d, n]).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (YgConfig, YgProblem, YgNoise, YgOutputs, YgState, check,
+                   MODEL_GAUSS, MODEL_LINEAR, MODEL_LV, EQ_EXACT, EQ_ISCLOSE,
+                   NOISE_PHILOX, NOISE_INJECT, NOISE_RECORD)
+
+_MODEL = {'gauss': MODEL_GAUSS, 'linear': MODEL_LINEAR, 'lv': MODEL_LV}
+_EQ = {'exact': EQ_EXACT, 'isclose': EQ_ISCLOSE}
+_dp = C.POINTER(C.c_double)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class LoweredProblem:
+    """The plain-array form of a (hierarchy of) Bayesian model(s) + proposal, i.e.
+    what ChainBuilder.build_method() (reference chain/builder.py:72-83) boils down to.
+
+    meta:   model ('gauss'|'linear'|'lv'), dim, levels (1|2), J, eq ('exact'|'isclose')
+    arrays: prop_L[d,d] and per level l: L{l}_g_mean/g_prec/g_logconst (gauss),
+            L{l}_data/noise_prec/prior_mean/prior_prec (+ L{l}_G/b | L{l}_design/lv=[alpha,gamma,T,N])
+    """
+
+    def __init__(self, meta, arrays):
+        self.model = meta['model']
+        self.dim = int(meta['dim'])
+        self.levels = int(meta['levels'])
+        self.J = int(meta.get('J', 1))
+        self.eq = meta.get('eq', 'exact')
+        if self.model not in _MODEL:
+            raise NotImplementedError(
+                f"model {self.model!r} has no device implementation; the backend accepts Gaussian targets, "
+                "linear models and the Lotka-Volterra RK4 model only (no CPU fallback)")
+        self.arrays = {k: _f64(v) for k, v in arrays.items()
+                       if k == 'prop_L' or k.startswith('L0_') or k.startswith('L1_')}
+        if 'prop_L' not in self.arrays:
+            raise ValueError("Proposal Covariance not set")
+
+    def c_struct(self):
+        pb = YgProblem()
+        a = self.arrays
+        pb.prop_L = a['prop_L'].ctypes.data_as(_dp)
+        for l in range(self.levels):
+            lv = pb.level[l]
+            pre = f"L{l}_"
+            for f in ("g_mean", "g_prec", "data", "noise_prec", "prior_mean", "prior_prec", "G", "b", "design"):
+                if pre + f in a:
+                    setattr(lv, f, a[pre + f].ctypes.data_as(_dp))
+            if pre + "g_logconst" in a:
+                lv.g_logconst = float(np.asarray(a[pre + "g_logconst"]).reshape(-1)[0])
+            if pre + "data" in a:
+                lv.n_data, lv.data_dim = (int(x) for x in a[pre + "data"].shape)
+            if pre + "lv" in a:
+                p = a[pre + "lv"]
+                lv.alpha, lv.gamma, lv.T, lv.rk4_steps = float(p[0]), float(p[1]), float(p[2]), int(p[3])
+        return pb
+
+
+class ChainEnsemble:
+    """n_chains independent chains of one problem on one device."""
+
+    def __init__(self, problem, n_chains, device=0, seed=0, chain_offset=0,
+                 adaptive=None, blocks_per_sm=0, threads_per_block=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BackendUnavailable("no CUDA device visible: the batched-chain backend has no CPU fallback")
+        self.problem = problem
+        self.n_chains = int(n_chains)
+        self.dim = problem.dim
+        self.levels = problem.levels
+        self.J = problem.J if problem.levels == 2 else 1
+        self.device = torch.device('cuda', int(device))
+        cfg = YgConfig()
+        cfg.abi_version = _lib.YG_ABI_VERSION
+        cfg.device = int(device)
+        cfg.n_chains = self.n_chains
+        cfg.chain_offset = int(chain_offset)
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.model = _MODEL[problem.model]
+        cfg.dim = problem.dim
+        cfg.n_levels = problem.levels
+        cfg.sub_chain_length = self.J
+        cfg.eq_mode = _EQ[problem.eq]
+        cfg.blocks_per_sm = int(blocks_per_sm)
+        cfg.threads_per_block = int(threads_per_block)
+        if adaptive:
+            cfg.adaptive = 1
+            cfg.am_idle_steps = int(adaptive.get('idle', 0))
+            cfg.am_collection_steps = int(adaptive.get('collection', 100))
+            cfg.am_refresh = int(adaptive.get('refresh', 1))
+            cfg.am_eps = float(adaptive.get('eps', 1e-4))
+            cfg.am_scale = float(adaptive.get('scale', 0.0))
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(self.lib.yg_create(C.byref(cfg), C.byref(self._h)))
+        pb = problem.c_struct()
+        check(self.lib.yg_set_problem(self._h, C.byref(pb)))
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _empty(self, *shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.yg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, theta0):
+        """theta0: [n_chains, d] (or [d], broadcast) host or device array."""
+        t = torch.as_tensor(np.asarray(theta0) if not torch.is_tensor(theta0) else theta0, dtype=torch.float64)
+        if t.dim() == 1:
+            t = t.reshape(1, -1).expand(self.n_chains, -1)
+        if tuple(t.shape) != (self.n_chains, self.dim):
+            raise ValueError(f"initial state must be [{self.n_chains}, {self.dim}], got {tuple(t.shape)}")
+        soa = t.to(self.device).t().contiguous()            # [d, n]
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_set_state(self._h, C.c_void_p(soa.data_ptr()), self._stream()))
+        return self
+
+    def run(self, n_steps, thin=1, samples=True, accepted=False, logpost=False, inject=None, record=False):
+        """Runs n_steps transitions of every chain.
+
+        inject: dict(z=[n_steps,J,d,n], u_c=[n_steps,J,n], u_f=[n_steps,n]) device or host arrays.
+        record: Philox noise, and the noise actually used is returned in the same layout.
+        Returns a dict of device tensors: samples [n_steps/thin, d, n], accepted [n_steps, n] uint8,
+        logpost [n_steps/thin, levels, n].
+        """
+        n, d, J = self.n_chains, self.dim, self.J
+        n_steps = int(n_steps)
+        out = YgOutputs()
+        res = {}
+        n_out = n_steps // thin
+        if samples:
+            res['samples'] = self._empty(n_out, d, n)
+            out.samples_dev = res['samples'].data_ptr()
+        if accepted:
+            res['accepted'] = self._empty(n_steps, n, dtype=torch.uint8)
+            out.accepted_dev = res['accepted'].data_ptr()
+        if logpost:
+            res['logpost'] = self._empty(n_out, self.levels, n)
+            out.logpost_dev = res['logpost'].data_ptr()
+        noise = YgNoise()
+        noise.mode = NOISE_PHILOX
+        keep = []
+        if inject is not None:
+            noise.mode = NOISE_INJECT
+            z = torch.as_tensor(inject['z'], dtype=torch.float64).to(self.device).contiguous()
+            u_f = torch.as_tensor(inject['u_f'], dtype=torch.float64).to(self.device).contiguous()
+            assert tuple(z.shape) == (n_steps, J, d, n), (tuple(z.shape), (n_steps, J, d, n))
+            assert tuple(u_f.shape) == (n_steps, n)
+            noise.z_dev, noise.u_f_dev = z.data_ptr(), u_f.data_ptr()
+            keep += [z, u_f]
+            if self.levels == 2:
+                u_c = torch.as_tensor(inject['u_c'], dtype=torch.float64).to(self.device).contiguous()
+                assert tuple(u_c.shape) == (n_steps, J, n)
+                noise.u_c_dev = u_c.data_ptr()
+                keep.append(u_c)
+        elif record:
+            noise.mode = NOISE_RECORD
+            res['z'] = torch.zeros(n_steps, J, d, n, dtype=torch.float64, device=self.device)
+            res['u_c'] = torch.full((n_steps, J, n), float('nan'), dtype=torch.float64, device=self.device)
+            res['u_f'] = torch.full((n_steps, n), float('nan'), dtype=torch.float64, device=self.device)
+            noise.z_dev, noise.u_c_dev, noise.u_f_dev = (res['z'].data_ptr(), res['u_c'].data_ptr(),
+                                                        res['u_f'].data_ptr())
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_run(self._h, n_steps, int(thin), C.byref(out), C.byref(noise), self._stream()))
+        res['_keep'] = keep
+        return res
+
+    def state(self):
+        n, d = self.n_chains, self.dim
+        st = YgState()
+        r = dict(theta=self._empty(d, n), logpost=self._empty(self.levels, n),
+                 n_accept=self._empty(n, dtype=torch.int64), w_mean=self._empty(d, n), w_m2=self._empty(d, d, n))
+        st.theta_dev, st.logpost_dev, st.n_accept_dev = r['theta'].data_ptr(), r['logpost'].data_ptr(), r['n_accept'].data_ptr()
+        st.w_mean_dev, st.w_m2_dev = r['w_mean'].data_ptr(), r['w_m2'].data_ptr()
+        if self.cfg.adaptive:
+            r['prop_L'] = self._empty(d, d, n)
+            st.prop_L_dev = r['prop_L'].data_ptr()
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_get_state(self._h, C.byref(st), self._stream()))
+        c = self.counters()
+        r['step_index'], r['welford_n'] = c['step_index'], c['welford_n']
+        return r
+
+    def load_state(self, r):
+        st = YgState()
+        keep = {k: r[k].to(self.device).contiguous() for k in
+                ('theta', 'logpost', 'n_accept', 'w_mean', 'w_m2', 'prop_L') if k in r}
+        st.theta_dev, st.logpost_dev = keep['theta'].data_ptr(), keep['logpost'].data_ptr()
+        if 'n_accept' in keep:
+            st.n_accept_dev = keep['n_accept'].data_ptr()
+        if 'w_mean' in keep:
+            st.w_mean_dev, st.w_m2_dev = keep['w_mean'].data_ptr(), keep['w_m2'].data_ptr()
+        if 'prop_L' in keep and self.cfg.adaptive:
+            st.prop_L_dev = keep['prop_L'].data_ptr()
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_load_state(self._h, C.byref(st), int(r.get('step_index', 0)),
+                                         int(r.get('welford_n', 0)), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+        return self
+
+    def counters(self):
+        buf = (C.c_int64 * 6)()
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_get_counters(self._h, buf, self._stream()))
+        keys = ('step_index', 'transitions', 'accepted', 'coarse_evals', 'fine_evals', 'welford_n')
+        c = dict(zip(keys, [int(x) for x in buf]))
+        if self.levels == 1:        # single level: level 0 IS the target
+            c['fine_evals'], c['coarse_evals'] = c['coarse_evals'], 0
+        return c
+
+    def logpost(self, level, theta):
+        t = torch.as_tensor(theta, dtype=torch.float64).to(self.device)
+        if t.dim() == 1:
+            t = t.reshape(1, -1)
+        m = t.shape[0]
+        soa = t.t().contiguous()
+        out = self._empty(m)
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_logpost(self._h, int(level), C.c_void_p(soa.data_ptr()), m,
+                                      C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def pooled_stats(self):
+        """Device vector of sufficient statistics (plain sums over local chains)."""
+        out = self._empty(int(self.lib.yg_pooled_len(self.dim)))
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_pooled_stats(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def last_launch(self):
+        g, b, s, l = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        check(self.lib.yg_last_launch(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(l)))
+        return dict(grid=g.value, block=b.value, smem=s.value, launches=l.value)
+
+
+def iat_ess(samples, method='max', sokal=5.0):
+    """samples: device tensor [n_samples, d, n_chains] -> (iat[n_chains], ess[n_chains]) int64 tensors.
+    Restates integrated_autocorrelation (postprocessing/autocorrelation.py:92-140) per chain."""
+    lib = _lib.load()
+    assert samples.is_cuda and samples.dtype == torch.float64 and samples.dim() == 3
+    samples = samples.contiguous()
+    ns, d, n = samples.shape
+    iat = torch.empty(n, dtype=torch.int64, device=samples.device)
+    ess = torch.empty(n, dtype=torch.int64, device=samples.device)
+    with torch.cuda.device(samples.device):
+        st = C.c_void_p(torch.cuda.current_stream(samples.device).cuda_stream)
+        check(lib.yg_iat_ess(C.c_void_p(samples.data_ptr()), ns, d, n, 1 if method == 'max' else 0,
+                             float(sokal), C.c_void_p(iat.data_ptr()), C.c_void_p(ess.data_ptr()), st))
+    return iat, ess
+
+
+def split_moments(samples):
+    lib = _lib.load()
+    samples = samples.contiguous()
+    ns, d, n = samples.shape
+    hm = torch.empty(2, d, n, dtype=torch.float64, device=samples.device)
+    hv = torch.empty(2, d, n, dtype=torch.float64, device=samples.device)
+    with torch.cuda.device(samples.device):
+        st = C.c_void_p(torch.cuda.current_stream(samples.device).cuda_stream)
+        check(lib.yg_split_moments(C.c_void_p(samples.data_ptr()), ns, d, n, C.c_void_p(hm.data_ptr()),
+                                   C.c_void_p(hv.data_ptr()), st))
+    return hm, hv
+
+
+def fp64_peak_tflops(device=0, ms=20.0):
+    lib = _lib.load()
+    out = C.c_double()
+    check(lib.yg_fp64_peak(int(device), float(ms), C.byref(out)))
+    return out.value
