@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batched-chain backend.
+
+Metric (BASELINE.json): Lotka-Volterra two-level delayed-acceptance chain-steps/s
+(and ESS/s), weak-scaled: 65,536 chains per GPU (= C5's 524,288 chains at 8 GPUs).
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm
+  python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port, all host threads)
+  torchrun ... bench.py --gpus N ...                        # one rank per GPU, NCCL
+
+A "step" is one pass of the hot path over the whole ensemble: one yg_run launch
+of `--transitions` (default 50) Metropolis-Hastings transitions of every chain.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import bench_problems as bp     # noqa: E402
+
+CHAINS_PER_GPU = 65536
+METRIC = "LV two-level delayed-acceptance chain-steps/s"
+UNIT = "chain-steps/s"
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "C5 example_inference_lotkaVolterra_twoLevel: LV RK4 forward (Nc=64 coarse / Nf=512 fine, "
+                    "nData=10 design points, T=10), Gaussian likelihood (var 0.04), prior N(0,1.4 I), "
+                    "base proposal 0.1 I, sub-chain J=3, theta0 = truth + 0.05 N(0,I)",
+        "chains_per_gpu": args.chains,
+        "total_chains": args.chains * n_gpus,
+        "transitions_per_step": args.transitions,
+        "parallelism": f"chains sharded, {n_gpus} x {args.chains}, no data-path collective",
+        "l2": "L2 flushed (512 MiB write) between timed iterations; the per-chain state (4 MiB) is smaller than L2",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for (t, line) in self.rows:
+            if t < t0 - 0.05 or t > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port (C, OpenMP) on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_chain_steps_per_s(meta, arrays, target_seconds, seed=11):
+    """Times oracle/yagre_oracle.c (yo_run_philox) on all host threads over a bounded sample
+    of the same workload: chains x transitions grown until about target_seconds of work."""
+    from oracle import cport
+    pb = cport.Problem(meta, arrays)
+    threads = cport.num_threads()
+    n_chains, n_tr = max(8 * threads, 64), 20
+    th0 = bp.lv_initial_states(n_chains)
+    t = time.perf_counter()
+    cport.run_philox(pb, th0, seed, n_tr, store=False)
+    dt = time.perf_counter() - t
+    rate = n_chains * n_tr / dt
+    n_tr = int(max(20, min(2000, target_seconds * rate / n_chains)))
+    t = time.perf_counter()
+    r = cport.run_philox(pb, th0, seed, n_tr, store=False)
+    dt = time.perf_counter() - t
+    return dict(value=n_chains * n_tr / dt, seconds=dt, threads=threads, chains=n_chains, transitions=n_tr,
+                accept=float(r["n_accept"].sum()) / (n_chains * n_tr))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    meta, arrays = bp.lv_problem(True)
+    cfg = workload_config(args, args.gpus)
+    times, units, info = [], [], None
+    for i in range(args.warmup + args.steps):
+        info = cpu_chain_steps_per_s(meta, arrays, args.cpu_seconds / max(args.steps, 1), seed=11 + i)
+        if i >= args.warmup:
+            times.append(info["seconds"]); units.append(info["chains"] * info["transitions"])
+    value = sum(units) / sum(times)
+    sample = (f"{info['chains']} chains x {info['transitions']} transitions per step, same problem/noise keying, "
+              f"oracle/yagre_oracle.c (C restatement of the reference step, -O2 -ffp-contract=off, OpenMP)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python (~40 chain-steps/s/core with an RK4 plugin, BASELINE.md); "
+                "it cannot travel to the GPU box, so this arm times the C port of the same algorithm",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem, fp64_peak_tflops, iat_ess
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local)
+    n_gpus = world
+
+    meta, arrays = bp.lv_problem(True)
+    pb = LoweredProblem(meta, arrays)
+    nc, S = args.chains, args.transitions
+    offset = rank * nc
+    ens = ChainEnsemble(pb, nc, device=local, seed=args.seed, chain_offset=offset)
+    th0 = bp.lv_initial_states(nc, chain_offset=offset)
+    ens.set_state(th0)
+    ens.run(args.burnin, samples=False)                       # burn-in so the timed steps are in stationarity
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    pooled = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(timed):
+        nonlocal pooled
+        flush.fill_(1)                                        # L2 flush between iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ens.run(S, samples=False)
+        if world > 1:                                         # pooled moments / R-hat statistics: the only collective
+            pooled = ens.pooled_stats()
+            dist.all_reduce(pooled)
+        e1.record()
+        return (e0, e1)
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    c0 = ens.counters()
+    l0 = ens.last_launch()["launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t0 = time.time()
+    evs = [one_step(True) for _ in range(args.steps)]
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms = [a.elapsed_time(b) for (a, b) in evs]
+    total_ms = float(sum(ms))
+    c1 = ens.counters()
+    launches = ens.last_launch()["launches"] - l0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    evals = torch.tensor([c1["coarse_evals"] - c0["coarse_evals"], c1["fine_evals"] - c0["fine_evals"],
+                          c1["accepted"] - c0["accepted"], launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(evals)
+    total_ms_max = float(t.item())
+    coarse_ev, fine_ev, n_acc, launches_all = [float(x) for x in evals.tolist()]
+    units = float(nc) * n_gpus * S * args.steps
+    value = units / (total_ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (lv_mh_kernel): FP64 pipe ---------------------------------
+    flops = bp.lv_flops_per_eval(meta["n_data"], meta["Nc"]) * coarse_ev + \
+        bp.lv_flops_per_eval(meta["n_data"], meta["Nf"]) * fine_ev
+    peak = fp64_peak_tflops(local, 30.0)
+    achieved = flops / n_gpus / (total_ms_max * 1e-3) / 1e12          # per GPU
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "kernel": "lv_mh_kernel<true>", "launch_ms": total_ms_max / args.steps,
+                "algorithmic_flop_per_launch": flops / n_gpus / args.steps,
+                "peak_source": "yg_fp64_peak: DFMA / RK4-step micro-benchmarks measured live on this GPU (best of "
+                               "variants); MEASURED_PEAKS.json has no fp64 entry",
+                "forward_evals_per_transition": {"coarse": coarse_ev / units, "fine": fine_ev / units}}
+
+    # ---- end to end through the public API: host theta0 in, host trajectory out ---------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = torch.from_numpy(th0).pin_memory()
+        host_out = torch.empty((S, 2, nc), dtype=torch.float64).pin_memory()
+        host_acc = torch.empty((nc,), dtype=torch.int64).pin_memory()
+        e_ms = []
+        for i in range(2 + max(3, args.steps // 4)):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ens.set_state(host_in.to(dev, non_blocking=True))           # H2D + log-posterior of the start state
+            out = ens.run(S, samples=True)
+            host_out.copy_(out["samples"], non_blocking=True)           # D2H trajectory
+            host_acc.copy_(ens.state()["n_accept"], non_blocking=True)  # D2H acceptance counts
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                e_ms.append(e0.elapsed_time(e1))
+        et = torch.tensor([float(np.mean(e_ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(nc) * n_gpus * S / (float(et.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8 + nc * 8),
+               "ms_per_step": float(et.item()),
+               "path": "ChainEnsemble.set_state(host theta0) + run(S, samples) + trajectory and accept counts to pinned host"}
+
+    # ---- ESS/s: the sampling run of the example (5,000 steps, burn-in 100), IAT on the device --------
+    ess = None
+    if not args.no_ess:
+        ens.set_state(th0)
+        torch.cuda.synchronize(dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = ens.run(args.ess_steps, samples=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        run_ms = e0.elapsed_time(e1)
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        iat, ess_c = iat_ess(out["samples"][args.ess_burnin:], "max")
+        e3.record()
+        torch.cuda.synchronize(dev)
+        tt = torch.tensor([run_ms, e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+        ss = torch.tensor([float(ess_c.sum().item()), float(iat.double().sum().item())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ss)
+        ess = {"ess_per_s": float(ss[0].item()) / (float(tt[0].item()) * 1e-3), "ensemble_ess": float(ss[0].item()),
+               "mean_iat_max": float(ss[1].item()) / (nc * n_gpus), "chain_length": args.ess_steps,
+               "burn_in": args.ess_burnin, "sampling_ms": float(tt[0].item()), "iat_kernel_ms": float(tt[1].item()),
+               "definition": "per chain (N - burnIn) // IAT_max (example_inference_lotkaVolterra_twoLevel.py:117-118,132), "
+                             "summed over chains / sampling wall time (burn-in included)"}
+        del out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu:
+        info = cpu_chain_steps_per_s(meta, arrays, args.cpu_seconds)
+        cpu = {"value": info["value"], "unit": UNIT, "cores": info["threads"], "kind": "port",
+               "sample": f"{info['chains']} chains x {info['transitions']} transitions of the same workload "
+                         f"({info['seconds']:.1f} s), oracle/yagre_oracle.c with OpenMP over chains",
+               "accept_rate": info["accept"]}
+
+    # sample write-back roofline (secondary bound): bytes of the e2e/ESS path per chain-step = 8 d
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus),
+        "accept_rate": n_acc / units,
+        "roofline": roofline,
+        "roofline_hbm": {"bound": "hbm", "achieved": (ess and 16.0 * nc * args.ess_steps / (ess["sampling_ms"] * 1e-3) / 1e9),
+                         "peak": hbm_peak or 6650.0, "unit": "GB/s",
+                         "peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback",
+                         "note": "sample write-back (16 B per stored chain-step) during the ESS sampling run; far from "
+                                 "the bound by design: the path is FP64-compute bound"},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "ess": ess,
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "launch": ens.last_launch(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--transitions", type=int, default=50, help="MH transitions of every chain per bench step")
+    ap.add_argument("--burnin", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--ess-steps", type=int, default=5000)
+    ap.add_argument("--ess-burnin", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

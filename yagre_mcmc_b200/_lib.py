@@ -47,7 +47,7 @@ class YgConfig(C.Structure):
                 ("am_refresh", C.c_int32), ("_pad0", C.c_int32),
                 ("am_eps", C.c_double), ("am_scale", C.c_double),
                 ("blocks_per_sm", C.c_int32), ("threads_per_block", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("rk4_segment", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class YgNoise(C.Structure):

@@ -10,6 +10,7 @@
 //   Welford moments       statistics/estimation.py:4-58
 // R-hat and pooling do not exist in the reference (single chain); they are new.
 #include "ensemble.h"
+#include "lv_model.cuh"
 #include <math_constants.h>
 
 namespace {
@@ -183,7 +184,10 @@ __global__ void pooled_stage2(const double *partials, int n_part, int len, doubl
     }
 }
 
-// DFMA micro-benchmark: 8 independent dependent-chains per thread, 1024 resident threads/SM.
+// FP64-pipe micro-benchmarks, 1024 resident threads/SM.  Variant 0: eight independent
+// DFMA chains per thread.  Variant 1: four interleaved LV RK4 steps per thread (the hot
+// loop's own instruction mix: 30 FP64-pipe instructions per step, DFMA/DMUL/DADD).  Both
+// count 2 flop per FP64-pipe instruction, i.e. they measure the DFMA-equivalent peak.
 __global__ void __launch_bounds__(256, 4) dfma_peak_kernel(double *sink, int iters, double a, double b)
 {
     double v0 = threadIdx.x * 1e-3, v1 = v0 + 1.0, v2 = v0 + 2.0, v3 = v0 + 3.0;
@@ -198,6 +202,25 @@ __global__ void __launch_bounds__(256, 4) dfma_peak_kernel(double *sink, int ite
     }
     const double s = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
     if (s == 123.456) sink[0] = s;                      // keeps the chains live
+}
+
+__global__ void __launch_bounds__(256, 4) rk4_peak_kernel(double *sink, int iters, double b0, double d0)
+{
+    LvRates r[4];
+    double x[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        r[i] = lv_rates(0.8, 0.4, 10.0, 512, b0 + 1e-3 * (threadIdx.x + i), d0 + 1e-3 * i);
+        x[i] = 1.0 + 1e-3 * threadIdx.x;
+        y[i] = 0.8 + 1e-3 * i;
+    }
+#pragma unroll 1
+    for (int s = 0; s < iters; s++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) lv_rk4_step(r[i], x[i], y[i]);
+    }
+    const double s = (x[0] + y[0]) + (x[1] + y[1]) + (x[2] + y[2]) + (x[3] + y[3]);
+    if (s == 1.2345) sink[0] = s;
 }
 
 }  // namespace
@@ -268,19 +291,24 @@ extern "C" int yg_fp64_peak(int32_t device, double ms, double *tflops_out)
     YG_CUDA_CHECK(cudaEventCreate(&e0));
     YG_CUDA_CHECK(cudaEventCreate(&e1));
     const int grid = sms * 4, threads = 256;
-    int iters = 2048;
     double best = 0.0;
-    float t = 0.f;
-    // calibrate the iteration count to about `ms` per launch, then take the best of 5
-    for (int rep = 0; rep < 7; rep++) {
-        YG_CUDA_CHECK(cudaEventRecord(e0));
-        dfma_peak_kernel<<<grid, threads>>>(sink, iters, 0.999999, 1e-9);
-        YG_CUDA_CHECK(cudaEventRecord(e1));
-        YG_CUDA_CHECK(cudaEventSynchronize(e1));
-        YG_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
-        const double flops = 2.0 * 64.0 * (double)iters * (double)grid * threads;
-        if (rep >= 2) best = std::max(best, flops / (t * 1e-3) / 1e12);
-        if (rep < 2 && t > 0.f) iters = (int)std::max(256.0, std::min(4.0e6, iters * (ms > 0 ? ms : 20.0) / t));
+    for (int variant = 0; variant < 2; variant++) {
+        // FP64-pipe instructions per thread per iteration: 64 DFMA, or 4 RK4 steps x 30
+        const double per_iter = variant == 0 ? 64.0 : 120.0;
+        int iters = 2048;
+        float t = 0.f;
+        // calibrate the iteration count to about `ms` per launch, then take the best of 5
+        for (int rep = 0; rep < 7; rep++) {
+            YG_CUDA_CHECK(cudaEventRecord(e0));
+            if (variant == 0) dfma_peak_kernel<<<grid, threads>>>(sink, iters, 0.999999, 1e-9);
+            else rk4_peak_kernel<<<grid, threads>>>(sink, iters, 0.4, 0.6);
+            YG_CUDA_CHECK(cudaEventRecord(e1));
+            YG_CUDA_CHECK(cudaEventSynchronize(e1));
+            YG_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+            const double flops = 2.0 * per_iter * (double)iters * (double)grid * threads;
+            if (rep >= 2) best = std::max(best, flops / (t * 1e-3) / 1e12);
+            if (rep < 2 && t > 0.f) iters = (int)std::max(256.0, std::min(4.0e6, iters * (ms > 0 ? ms : 20.0) / t));
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

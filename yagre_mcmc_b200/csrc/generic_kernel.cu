@@ -88,6 +88,7 @@ YG_DEVFN double logpost_any(const DevProblemHeader *pb, int lvl, const double (&
         sum = np_stream_sum(nD, [&](int n) {
             double X = design[2 * n], Y = design[2 * n + 1];
             lv_integrate(rates, Lv.rk4_steps, X, Y);
+            lv_finite_or_inf(X, Y);
             const double r[2] = {X - data[2 * n], Y - data[2 * n + 1]};
             return quad_form<2>(Lv.noise_prec, 2, r, 2);
         });

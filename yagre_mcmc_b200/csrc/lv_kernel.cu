@@ -72,7 +72,7 @@ YG_DEVFN void tma_stage_blob(void *dst, const void *src, uint32_t bytes, uint64_
 }
 
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(256, 4) lv_mh_kernel(const RunArgs a, const int cmax)
+__global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const int cmax, const int seg_len)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(256, 4) lv_mh_kernel(const RunArgs a, const in
     off += sizeof(double) * SmemLayout::NDBL * cmax;
     const int nd_max = max(a.problem->lvl[0].n_data, TWO_LEVEL ? a.problem->lvl[1].n_data : 0);
     double *q = reinterpret_cast<double *>(smem_raw + off);                // [n_data][cmax]
+    off += sizeof(double) * (size_t)nd_max * cmax;
+    double *sx = reinterpret_cast<double *>(smem_raw + off);               // [n_data * cmax] ODE state between
+    off += sizeof(double) * (size_t)nd_max * cmax;                         //   segments, indexed by item
+    double *sy = reinterpret_cast<double *>(smem_raw + off);
     off += sizeof(double) * (size_t)nd_max * cmax;
     unsigned long long *nacc = reinterpret_cast<unsigned long long *>(smem_raw + off);   // [cmax]
     off += sizeof(unsigned long long) * cmax;
@@ -112,32 +116,61 @@ __global__ void __launch_bounds__(256, 4) lv_mh_kernel(const RunArgs a, const in
     const int64_t N = a.n_chains;
 
     // ---- one phase of forward evaluations over the compacted list ---------------
+    // Work unit = (item, segment): item = (active chain, design point), segment = `seg_len`
+    // consecutive RK4 steps.  Units are ordered segment-major and dealt to the threads in
+    // rounds of R = min(blockDim, nItems) units, so consecutive segments of one item always
+    // fall into different rounds (their state travels through sx/sy) and only the LAST round
+    // of a phase is partially filled -- the quantisation loss is < R / nUnits instead of
+    // < blockDim / nItems.
     auto eval_phase = [&](int lvl, int cur) {
         const DevLevel &Lv = pb->lvl[lvl];
         const int na = nact[cur];
         const int nD = Lv.n_data;
         const int nItems = na * nD;
+        const int Nrk = Lv.rk4_steps;
+        const int nSeg = (Nrk + seg_len - 1) / seg_len;
+        const int nUnits = nItems * nSeg;
+        const int R = min(nthr, nItems);
         const int *lst = list0 + cur * cmax;
         const double *design = tail + Lv.design_off;
         const double *data = tail + Lv.data_off;
         const double P00 = Lv.noise_prec[0], P01 = Lv.noise_prec[1], P10 = Lv.noise_prec[2], P11 = Lv.noise_prec[3];
+        const double h = Lv.T / (double)Nrk;
+        const double ha = h * Lv.alpha, hg = h * Lv.gamma;
         if (tid == 0) {
             nact[cur ^ 1] = 0;
             blk_cnt[2 + lvl] += (unsigned long long)na;
         }
-        for (int it = tid; it < nItems; it += nthr) {
-            const int ai = it % na, n = it / na;
-            const int c = lst[ai];
-            const LvRates r = lv_rates(Lv.alpha, Lv.gamma, Lv.T, Lv.rk4_steps, CH(BETA, c), CH(DELTA, c));
-            double x = design[2 * n], y = design[2 * n + 1];
-            lv_integrate(r, Lv.rk4_steps, x, y);
-            const double r0 = x - data[2 * n], r1 = y - data[2 * n + 1];
-            // r' P r with P applied first; exact zeros skipped (diagonal noise, inf-safe)
-            double t0 = P00 * r0;
-            if (P01 != 0.0) t0 = fma(P01, r1, t0);
-            double t1 = (P10 != 0.0) ? P10 * r0 : 0.0;
-            t1 = (P10 != 0.0) ? fma(P11, r1, t1) : P11 * r1;
-            q[n * cmax + c] = fma(r1, t1, r0 * t0);
+        for (int u0 = 0; u0 < nUnits; u0 += R) {
+            const int u = u0 + tid;
+            if (tid < R && u < nUnits) {
+                const int seg = u / nItems, it = u - seg * nItems;
+                const int n = it / na, ai = it - n * na;
+                const int c = lst[ai];
+                LvRates r;
+                r.ha = ha; r.hg = hg;
+                r.hb = h * CH(BETA, c);
+                r.hd = h * CH(DELTA, c);
+                double x, y;
+                if (seg == 0) { x = design[2 * n]; y = design[2 * n + 1]; }
+                else { x = sx[it]; y = sy[it]; }
+                lv_integrate(r, min(seg_len, Nrk - seg * seg_len), x, y);
+                if (seg + 1 < nSeg) {
+                    sx[it] = x; sy[it] = y;
+                } else {
+                    // non-finite forward output -> +inf (policy of the oracle's RK4 plugin)
+                    x = isfinite(x) ? x : CUDART_INF;
+                    y = isfinite(y) ? y : CUDART_INF;
+                    const double r0 = x - data[2 * n], r1 = y - data[2 * n + 1];
+                    // r' P r with P applied first; exact zeros skipped (diagonal noise, inf-safe)
+                    double t0 = P00 * r0;
+                    if (P01 != 0.0) t0 = fma(P01, r1, t0);
+                    double t1 = (P10 != 0.0) ? P10 * r0 : 0.0;
+                    t1 = (P10 != 0.0) ? fma(P11, r1, t1) : P11 * r1;
+                    q[n * cmax + c] = fma(r1, t1, r0 * t0);
+                }
+            }
+            if (u0 + R < nUnits) __syncthreads();
         }
     };
 
@@ -335,7 +368,7 @@ size_t lv_smem_bytes(const yg_ensemble *e, int cmax, int nd_max)
 {
     size_t off = (e->h_problem.size() + 15u) & ~size_t(15);
     off += sizeof(double) * SmemLayout::NDBL * cmax;
-    off += sizeof(double) * (size_t)nd_max * cmax;
+    off += sizeof(double) * (size_t)nd_max * cmax * 3;     // q, sx, sy
     off += sizeof(unsigned long long) * cmax;
     off += sizeof(int) * 2 * cmax;
     off += (cmax + 15) & ~15;
@@ -352,8 +385,8 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     const int nd_max = std::max(hp->lvl[0].n_data, two ? hp->lvl[1].n_data : 0);
     int threads = e->cfg.threads_per_block > 0 ? e->cfg.threads_per_block : 256;
     int bps = e->cfg.blocks_per_sm > 0 ? e->cfg.blocks_per_sm : 4;
-    if (threads % 32 || threads > 256) {
-        yg_set_error("threads_per_block must be a multiple of 32 and <= 256 (got %d)", threads);
+    if (threads % 32 || threads > 512) {
+        yg_set_error("threads_per_block must be a multiple of 32 and <= 512 (got %d)", threads);
         return YG_ERR_INVALID;
     }
     int64_t grid64 = std::min<int64_t>((int64_t)e->sm_count * bps, a.n_chains);
@@ -362,7 +395,7 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     int64_t share = (a.n_chains + grid - 1) / grid;
     const size_t budget = (size_t)(220 * 1024) / bps;
     const size_t fixed = lv_smem_bytes(e, 0, nd_max);
-    const size_t per_chain = sizeof(double) * (SmemLayout::NDBL + nd_max) + 8 + 8 + 1;
+    const size_t per_chain = sizeof(double) * (SmemLayout::NDBL + 3 * nd_max) + 8 + 8 + 1;
     int64_t cap = fixed < budget ? (int64_t)((budget - fixed) / per_chain) : 0;
     if (cap < 1) {
         yg_set_error("problem blob too large for shared memory (%zu bytes)", fixed);
@@ -372,7 +405,8 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     const size_t smem = lv_smem_bytes(e, cmax, nd_max);
     auto kern = two ? lv_mh_kernel<true> : lv_mh_kernel<false>;
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(a, cmax);
+    const int seg_len = e->cfg.rk4_segment > 0 ? e->cfg.rk4_segment : 32;
+    kern<<<grid, threads, smem, st>>>(a, cmax, seg_len);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
     e->last_block = threads;

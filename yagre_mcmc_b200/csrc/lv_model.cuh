@@ -54,7 +54,7 @@ YG_DEVFN void lv_rk4_step(const LvRates &r, double &x, double &y)
     y = fma(sixth, ky, ay);
 }
 
-// Integrates N steps; non-finite outputs are mapped to +inf (=> logL = -inf =>
+// Integrates N steps.  The caller maps non-finite END states to +inf (=> logL = -inf =>
 // rejected by the unchanged acceptance rule), the policy of the oracle plugin.
 YG_DEVFN void lv_integrate(const LvRates &r, int N, double &x, double &y)
 {
@@ -68,6 +68,10 @@ YG_DEVFN void lv_integrate(const LvRates &r, int N, double &x, double &y)
     }
 #pragma unroll 1
     for (; i < N; i++) lv_rk4_step(r, x, y);
+}
+
+YG_DEVFN void lv_finite_or_inf(double &x, double &y)
+{
     x = isfinite(x) ? x : CUDART_INF;
     y = isfinite(y) ? y : CUDART_INF;
 }

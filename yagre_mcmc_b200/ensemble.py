@@ -71,7 +71,7 @@ class ChainEnsemble:
     """n_chains independent chains of one problem on one device."""
 
     def __init__(self, problem, n_chains, device=0, seed=0, chain_offset=0,
-                 adaptive=None, blocks_per_sm=0, threads_per_block=0):
+                 adaptive=None, blocks_per_sm=0, threads_per_block=0, rk4_segment=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.BackendUnavailable("no CUDA device visible: the batched-chain backend has no CPU fallback")
@@ -94,6 +94,7 @@ class ChainEnsemble:
         cfg.eq_mode = _EQ[problem.eq]
         cfg.blocks_per_sm = int(blocks_per_sm)
         cfg.threads_per_block = int(threads_per_block)
+        cfg.rk4_segment = int(rk4_segment)
         if adaptive:
             cfg.adaptive = 1
             cfg.am_idle_steps = int(adaptive.get('idle', 0))
