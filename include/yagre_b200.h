@@ -126,7 +126,7 @@ typedef struct yg_config {
     double am_scale;            /* s; <= 0 selects 2.4^2 / d */
     int32_t blocks_per_sm;      /* 0 = default; tuning knob of the LV kernel */
     int32_t threads_per_block;  /* 0 = default */
-    int32_t rk4_segment;        /* 0 = default (32): RK4 steps per work unit of the LV kernel */
+    int32_t rk4_segment;        /* 0 = default (128): RK4 steps per work unit of the LV kernel */
     int32_t reserved[5];
 } yg_config;
 

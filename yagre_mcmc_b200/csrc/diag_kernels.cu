@@ -214,10 +214,11 @@ __global__ void __launch_bounds__(256, 4) rk4_peak_kernel(double *sink, int iter
         x[i] = 1.0 + 1e-3 * threadIdx.x;
         y[i] = 0.8 + 1e-3 * i;
     }
+    const LvConsts k = lv_consts();
 #pragma unroll 1
     for (int s = 0; s < iters; s++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) lv_rk4_step(r[i], x[i], y[i]);
+        for (int i = 0; i < 4; i++) lv_rk4_step(r[i], k, x[i], y[i]);
     }
     const double s = (x[0] + y[0]) + (x[1] + y[1]) + (x[2] + y[2]) + (x[3] + y[3]);
     if (s == 1.2345) sink[0] = s;

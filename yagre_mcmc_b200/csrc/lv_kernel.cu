@@ -71,8 +71,19 @@ YG_DEVFN void tma_stage_blob(void *dst, const void *src, uint32_t bytes, uint64_
     }
 }
 
+// u / d for 0 <= u < 2^24 via a float reciprocal and one correction step: two integer
+// divisions per work unit were a measurable share of the non-FP64 issue slots.
+YG_DEVFN int fast_div(int u, int d, float inv)
+{
+    int q = __float2int_rz(__int2float_rz(u) * inv);
+    const int r = u - q * d;
+    q += (r >= d) ? 1 : 0;
+    q -= (r < 0) ? 1 : 0;
+    return q;
+}
+
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const int cmax, const int seg_len)
+__global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const int cmax, const int seg_len)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -122,7 +133,7 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
     // fall into different rounds (their state travels through sx/sy) and only the LAST round
     // of a phase is partially filled -- the quantisation loss is < R / nUnits instead of
     // < blockDim / nItems.
-    auto eval_phase = [&](int lvl, int cur) {
+    auto eval_phase = [&](const int lvl, const int cur, const double h, const double ha, const double hg) {
         const DevLevel &Lv = pb->lvl[lvl];
         const int na = nact[cur];
         const int nD = Lv.n_data;
@@ -135,8 +146,7 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
         const double *design = tail + Lv.design_off;
         const double *data = tail + Lv.data_off;
         const double P00 = Lv.noise_prec[0], P01 = Lv.noise_prec[1], P10 = Lv.noise_prec[2], P11 = Lv.noise_prec[3];
-        const double h = Lv.T / (double)Nrk;
-        const double ha = h * Lv.alpha, hg = h * Lv.gamma;
+        const float inv_items = 1.0f / (float)nItems, inv_na = 1.0f / (float)na;
         if (tid == 0) {
             nact[cur ^ 1] = 0;
             blk_cnt[2 + lvl] += (unsigned long long)na;
@@ -144,8 +154,8 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
         for (int u0 = 0; u0 < nUnits; u0 += R) {
             const int u = u0 + tid;
             if (tid < R && u < nUnits) {
-                const int seg = u / nItems, it = u - seg * nItems;
-                const int n = it / na, ai = it - n * na;
+                const int seg = fast_div(u, nItems, inv_items), it = u - seg * nItems;
+                const int n = fast_div(it, na, inv_na), ai = it - n * na;
                 const int c = lst[ai];
                 LvRates r;
                 r.ha = ha; r.hg = hg;
@@ -200,6 +210,11 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
         return u;
     };
 
+#ifdef YG_TIMERS
+    long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long dbg_last = clock64();
+    const long long dbg_start = dbg_last;
+#endif
     int cur = 0;
     for (int64_t cb = cta_lo; cb < cta_hi; cb += cmax) {
         const int C = (int)min((int64_t)cmax, cta_hi - cb);
@@ -294,8 +309,18 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
                 }
                 __syncthreads();
                 // =============== forward evaluations =============================
-                eval_phase((TWO_LEVEL && j == J) ? 1 : 0, cur);
+#ifdef YG_TIMERS
+                const long long tA = clock64();
+                if (tid == 0) { dbg_t[0] += tA - dbg_last; dbg_t[4 + ((TWO_LEVEL && j == J) ? 1 : 0)] += nact[cur]; }
+#endif
+                // two inlined copies so that h, h*alpha, h*gamma are constant-bank operands
+                if (TWO_LEVEL && j == J) eval_phase(1, cur, a.lv_h[1], a.lv_ha[1], a.lv_hg[1]);
+                else eval_phase(0, cur, a.lv_h[0], a.lv_ha[0], a.lv_hg[0]);
                 __syncthreads();
+#ifdef YG_TIMERS
+                dbg_last = clock64();
+                if (tid == 0) dbg_t[1 + ((TWO_LEVEL && j == J) ? 1 : 0)] += dbg_last - tA;
+#endif
                 cur ^= 1;
             }
             // =============== commit the transition ===============================
@@ -360,6 +385,13 @@ __global__ void __launch_bounds__(512, 2) lv_mh_kernel(const RunArgs a, const in
         if (tid == 0) blk_cnt[0] += (unsigned long long)C * (unsigned long long)a.n_steps;
     }
     __syncthreads();
+#ifdef YG_TIMERS
+    if (tid == 0 && a.lp_out == nullptr && a.samples != nullptr) {   // debug: timers into the samples buffer
+        long long *o = reinterpret_cast<long long *>(a.samples) + 8 * blockIdx.x;
+        o[0] = dbg_t[0]; o[1] = dbg_t[1]; o[2] = dbg_t[2]; o[3] = clock64() - dbg_start;
+        o[4] = dbg_t[4]; o[5] = dbg_t[5]; o[6] = 0; o[7] = 0;
+    }
+#endif
     if (tid < 4 && blk_cnt[tid]) atomicAdd(&a.counters[tid], blk_cnt[tid]);
 #undef CH
 }
@@ -383,10 +415,18 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
     const bool two = e->cfg.n_levels == 2;
     const int nd_max = std::max(hp->lvl[0].n_data, two ? hp->lvl[1].n_data : 0);
-    int threads = e->cfg.threads_per_block > 0 ? e->cfg.threads_per_block : 256;
-    int bps = e->cfg.blocks_per_sm > 0 ? e->cfg.blocks_per_sm : 4;
-    if (threads % 32 || threads > 512) {
-        yg_set_error("threads_per_block must be a multiple of 32 and <= 512 (got %d)", threads);
+    // Default geometry (profiles/r01_lv_tuning.md): ONE persistent CTA per SM with up to 1024
+    // threads.  Several smaller CTAs per SM finish at very different times because the FP64
+    // issue arbiter is not fair between CTAs, which leaves SMs half empty towards the end.
+    int bps = e->cfg.blocks_per_sm > 0 ? e->cfg.blocks_per_sm : 1;
+    int threads = e->cfg.threads_per_block;
+    if (threads <= 0) {
+        const int64_t ctas = std::min<int64_t>((int64_t)e->sm_count * bps, a.n_chains);
+        const int64_t items = ((a.n_chains + ctas - 1) / ctas) * nd_max;
+        threads = (int)std::min<int64_t>(1024 / bps, std::max<int64_t>(128, (items + 31) / 32 * 32));
+    }
+    if (threads % 32 || threads > 1024) {
+        yg_set_error("threads_per_block must be a multiple of 32 and <= 1024 (got %d)", threads);
         return YG_ERR_INVALID;
     }
     int64_t grid64 = std::min<int64_t>((int64_t)e->sm_count * bps, a.n_chains);
@@ -403,10 +443,16 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     }
     const int cmax = (int)std::max<int64_t>(1, std::min<int64_t>(share, std::min<int64_t>(cap, 1024)));
     const size_t smem = lv_smem_bytes(e, cmax, nd_max);
+    RunArgs args = a;
+    for (int l = 0; l < e->cfg.n_levels; l++) {
+        args.lv_h[l] = hp->lvl[l].T / (double)hp->lvl[l].rk4_steps;
+        args.lv_ha[l] = args.lv_h[l] * hp->lvl[l].alpha;
+        args.lv_hg[l] = args.lv_h[l] * hp->lvl[l].gamma;
+    }
     auto kern = two ? lv_mh_kernel<true> : lv_mh_kernel<false>;
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int seg_len = e->cfg.rk4_segment > 0 ? e->cfg.rk4_segment : 32;
-    kern<<<grid, threads, smem, st>>>(a, cmax, seg_len);
+    const int seg_len = e->cfg.rk4_segment > 0 ? e->cfg.rk4_segment : 128;
+    kern<<<grid, threads, smem, st>>>(args, cmax, seg_len);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
     e->last_block = threads;
