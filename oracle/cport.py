@@ -27,7 +27,9 @@ class YoLevel(C.Structure):
 
 class YoProblem(C.Structure):
     _fields_ = [("model", C.c_int32), ("dim", C.c_int32), ("n_levels", C.c_int32), ("J", C.c_int32),
-                ("eq_mode", C.c_int32), ("_pad", C.c_int32), ("prop_L", _dp), ("level", YoLevel * 2)]
+                ("eq_mode", C.c_int32), ("_pad", C.c_int32), ("prop_L", _dp), ("level", YoLevel * 2),
+                ("adaptive", C.c_int32), ("am_refresh", C.c_int32), ("am_idle", C.c_int64),
+                ("am_collect", C.c_int64), ("am_eps", C.c_double), ("am_scale", C.c_double)]
 
 
 def build(force=False):
@@ -63,7 +65,7 @@ def _ptr(a):
 class Problem:
     """Keeps the numpy buffers alive next to the ctypes struct."""
 
-    def __init__(self, meta, arrays):
+    def __init__(self, meta, arrays, adaptive=None):
         self.meta = dict(meta)
         self.keep = {}
         pb = YoProblem()
@@ -72,6 +74,15 @@ class Problem:
         pb.n_levels = int(meta['levels'])
         pb.J = int(meta['J'])
         pb.eq_mode = EQ[meta.get('eq', 'exact')]
+        pb.am_refresh = 1
+        if adaptive:
+            pb.adaptive = 1
+            pb.am_idle = int(adaptive.get('idle', 0))
+            pb.am_collect = int(adaptive.get('collection', 100))
+            pb.am_refresh = int(adaptive.get('refresh', 1))
+            pb.am_eps = float(adaptive.get('eps', 1e-4))
+            sc = float(adaptive.get('scale', 0.0))
+            pb.am_scale = sc if sc > 0 else 2.4 * 2.4 / int(meta['dim'])
 
         def put(obj, field, key):
             if key in arrays:

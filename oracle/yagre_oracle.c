@@ -56,6 +56,10 @@ typedef struct yo_problem {
     int32_t model, dim, n_levels, J, eq_mode, _pad;
     const double *prop_L;      /* [d,d] lower triangular, p = s + L z (gaussian.py:61-66) */
     yo_level level[2];         /* level[n_levels-1] is the target */
+    /* adaptive Metropolis (single level; recurrence of DESIGN.md, parity UNPINNED vs the reference) */
+    int32_t adaptive, am_refresh;
+    int64_t am_idle, am_collect;
+    double am_eps, am_scale;
 } yo_problem;
 
 /* ---------------------------------------------------------------------- */
@@ -182,14 +186,14 @@ double yo_logpost(const yo_problem *pb, int lvl, const double *theta, int64_t *n
 /* ---------------------------------------------------------------------- */
 
 /* statistics/gaussian.py:61-66, covariance.py:51-52,84-86 */
-static void propose(const yo_problem *pb, const double *s, const double *z, double *p)
+static void propose(const yo_problem *pb, const double *L, const double *s, const double *z, double *p)
 {
     const int d = pb->dim;
     for (int i = 0; i < d; i++) {
         double acc = 0.0;
         int first = 1;
         for (int j = 0; j <= i; j++) {
-            double l = pb->prop_L[i * d + j];
+            double l = L[i * d + j];
             if (l != 0.0 || j == i) {
                 double t = l * z[j];
                 acc = first ? t : acc + t;
@@ -318,7 +322,37 @@ typedef struct {
     int64_t n_evals[2];
     int64_t w_n;                   /* Welford (estimation.py:36-53), fed the PRE-transition state */
     double w_mean[YO_MAX_DIM], w_m2[YO_MAX_DIM];
+    /* adaptive Metropolis: full-matrix Welford of the states from step am_idle on + current factor */
+    double am_mean[YO_MAX_DIM], am_m2[YO_MAX_DIM * YO_MAX_DIM], L[YO_MAX_DIM * YO_MAX_DIM];
 } chain_state;
+
+int yo_cholesky(const double *C, int d, double *L);
+
+/* chain/adaptive.py:55-60: update() runs in set_state(), i.e. BEFORE each proposal, with the
+ * current state.  Rule (ours): C = s (Cov + eps I) once am_collect states were collected. */
+static void am_update(const yo_problem *pb, chain_state *cs, int64_t t_idx)
+{
+    const int d = pb->dim;
+    if (t_idx < pb->am_idle) return;
+    const int64_t n_am = t_idx - pb->am_idle + 1;
+    double dl[YO_MAX_DIM], e[YO_MAX_DIM];
+    for (int i = 0; i < d; i++) {
+        dl[i] = cs->theta[i] - cs->am_mean[i];
+        cs->am_mean[i] += dl[i] / (double)n_am;
+        e[i] = cs->theta[i] - cs->am_mean[i];
+    }
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) cs->am_m2[i * d + j] += dl[i] * e[j];
+    if (n_am >= pb->am_collect && n_am >= 2 && ((n_am - pb->am_collect) % pb->am_refresh) == 0) {
+        double C[YO_MAX_DIM * YO_MAX_DIM], Ln[YO_MAX_DIM * YO_MAX_DIM];
+        for (int i = 0; i < d; i++)
+            for (int j = 0; j < d; j++) {
+                double cov = 0.5 * (cs->am_m2[i * d + j] + cs->am_m2[j * d + i]) / (double)(n_am - 1);
+                C[i * d + j] = pb->am_scale * (cov + ((i == j) ? pb->am_eps : 0.0));
+            }
+        if (yo_cholesky(C, d, Ln) == 0) memcpy(cs->L, Ln, sizeof(double) * d * d);
+    }
+}
 
 static void welford_update(chain_state *cs, int d)
 {
@@ -335,6 +369,7 @@ static void chain_init(const yo_problem *pb, chain_state *cs, const double *thet
 {
     memset(cs, 0, sizeof(*cs));
     memcpy(cs->theta, theta0, sizeof(double) * pb->dim);
+    memcpy(cs->L, pb->prop_L, sizeof(double) * pb->dim * pb->dim);
     for (int l = 0; l < pb->n_levels; l++)
         cs->lp[l] = yo_logpost(pb, l, cs->theta, &cs->n_evals[l]);
 }
@@ -348,8 +383,9 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
     double z[YO_MAX_DIM], p[YO_MAX_DIM];
     welford_update(cs, d);                               /* diagnostics.py:91-94 */
     if (pb->n_levels == 1) {
+        if (pb->adaptive) am_update(pb, cs, (int64_t)ns->step0 + n);
         get_z(pb, ns, n, 0, z);
-        propose(pb, cs->theta, z, p);
+        propose(pb, cs->L, cs->theta, z, p);
         if (param_equal(pb, p, cs->theta)) return 0;     /* metropolisHastings.py:60-61 */
         double lpp = yo_logpost(pb, 0, p, &cs->n_evals[0]);
         if (accept_rule(lpp - cs->lp[0], get_uf(ns, n))) {
@@ -364,7 +400,7 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
     memcpy(s, cs->theta, sizeof(double) * d);
     for (int j = 0; j < pb->J; j++) {                    /* coarse MRW sub-chain */
         get_z(pb, ns, n, j, z);
-        propose(pb, s, z, p);
+        propose(pb, cs->L, s, z, p);
         if (param_equal(pb, p, s)) continue;
         double lpp = yo_logpost(pb, 0, p, &cs->n_evals[0]);
         if (accept_rule(lpp - lpc_s, get_uc(pb, ns, n, j))) {

@@ -1,0 +1,3 @@
+from .mrw import MRWBuilder, MetropolisedRandomWalk
+from .mlda import MLDABuilder, MLDA
+from .am import AMBuilder, AdaptiveMetropolis
