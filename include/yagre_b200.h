@@ -60,7 +60,7 @@
 extern "C" {
 #endif
 
-#define YG_ABI_VERSION 1u
+#define YG_ABI_VERSION 2u
 #define YG_MAX_DIM 8           /* parameter dimension of the register-resident kernels */
 #define YG_MAX_DATA_DIM 8
 
@@ -152,6 +152,8 @@ typedef struct yg_state {
     double *w_mean_dev;         /* [d, n_chains]    Welford mean of the pre-transition states */
     double *w_m2_dev;           /* [d, d, n_chains] Welford second central moment (diagonal = WelfordAccumulator M2) */
     double *prop_L_dev;         /* [d, d, n_chains] current proposal factor (adaptive only) */
+    double *am_mean_dev;        /* [d, n_chains]    adaptive Metropolis running mean (adaptive only) */
+    double *am_m2_dev;          /* [d, d, n_chains] adaptive Metropolis second central moment (adaptive only) */
 } yg_state;
 
 const char *yg_last_error(void);

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyagre_b200.so")
 
-YG_ABI_VERSION = 1
+YG_ABI_VERSION = 2
 YG_MAX_DIM = 8
 YG_MAX_DATA_DIM = 8
 
@@ -61,7 +61,8 @@ class YgOutputs(C.Structure):
 
 class YgState(C.Structure):
     _fields_ = [("theta_dev", C.c_void_p), ("logpost_dev", C.c_void_p), ("n_accept_dev", C.c_void_p),
-                ("w_mean_dev", C.c_void_p), ("w_m2_dev", C.c_void_p), ("prop_L_dev", C.c_void_p)]
+                ("w_mean_dev", C.c_void_p), ("w_m2_dev", C.c_void_p), ("prop_L_dev", C.c_void_p),
+                ("am_mean_dev", C.c_void_p), ("am_m2_dev", C.c_void_p)]
 
 
 # every symbol include/yagre_b200.h declares: (restype, argtypes)

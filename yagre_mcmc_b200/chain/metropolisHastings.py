@@ -104,7 +104,7 @@ class MetropolisHastings:
         thin = self._thin
         pieces = []
         if self._store:
-            pieces.append(torch.as_tensor(np.ascontiguousarray(theta0.T), device=ens.device).unsqueeze(0))
+            pieces.append(torch.from_numpy(np.array(theta0.T, dtype=np.float64)).to(ens.device).unsqueeze(0))
         interval = self._verbosityController.print_interval(chainLength) if verbose else max(nTrans, 1)
         interval = max(thin, (interval // thin) * thin)
         done = 0

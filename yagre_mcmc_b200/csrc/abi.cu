@@ -386,6 +386,14 @@ extern "C" int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream)
         }
         YG_CUDA_CHECK(cudaMemcpyAsync(dst->prop_L_dev, e->prop_L, 8 * d * d * n, k, st));
     }
+    if (dst->am_mean_dev || dst->am_m2_dev) {
+        if (!e->cfg.adaptive) {
+            yg_set_error("am_mean_dev / am_m2_dev are per-chain state of adaptive ensembles only");
+            return YG_ERR_INVALID;
+        }
+        if (dst->am_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->am_mean_dev, e->am_mean, 8 * d * n, k, st));
+        if (dst->am_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->am_m2_dev, e->am_m2, 8 * d * d * n, k, st));
+    }
     return YG_OK;
 }
 
@@ -408,6 +416,10 @@ extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_i
     if (src->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_m2, src->w_m2_dev, 8 * d * d * n, k, st));
     if (src->prop_L_dev && e->cfg.adaptive)
         YG_CUDA_CHECK(cudaMemcpyAsync(e->prop_L, src->prop_L_dev, 8 * d * d * n, k, st));
+    if (src->am_mean_dev && e->cfg.adaptive)
+        YG_CUDA_CHECK(cudaMemcpyAsync(e->am_mean, src->am_mean_dev, 8 * d * n, k, st));
+    if (src->am_m2_dev && e->cfg.adaptive)
+        YG_CUDA_CHECK(cudaMemcpyAsync(e->am_m2, src->am_m2_dev, 8 * d * d * n, k, st));
     e->step_index = step_index;
     e->welford_n = welford_n;
     e->state_set = true;

@@ -129,7 +129,7 @@ class ChainEnsemble:
     # ------------------------------------------------------------------ state
     def set_state(self, theta0):
         """theta0: [n_chains, d] (or [d], broadcast) host or device array."""
-        t = torch.as_tensor(np.asarray(theta0) if not torch.is_tensor(theta0) else theta0, dtype=torch.float64)
+        t = theta0.to(torch.float64) if torch.is_tensor(theta0) else torch.from_numpy(np.array(theta0, dtype=np.float64))
         if t.dim() == 1:
             t = t.reshape(1, -1).expand(self.n_chains, -1)
         if tuple(t.shape) != (self.n_chains, self.dim):
@@ -197,8 +197,9 @@ class ChainEnsemble:
         st.theta_dev, st.logpost_dev, st.n_accept_dev = r['theta'].data_ptr(), r['logpost'].data_ptr(), r['n_accept'].data_ptr()
         st.w_mean_dev, st.w_m2_dev = r['w_mean'].data_ptr(), r['w_m2'].data_ptr()
         if self.cfg.adaptive:
-            r['prop_L'] = self._empty(d, d, n)
-            st.prop_L_dev = r['prop_L'].data_ptr()
+            r['prop_L'], r['am_mean'], r['am_m2'] = self._empty(d, d, n), self._empty(d, n), self._empty(d, d, n)
+            st.prop_L_dev, st.am_mean_dev, st.am_m2_dev = (r['prop_L'].data_ptr(), r['am_mean'].data_ptr(),
+                                                           r['am_m2'].data_ptr())
         with torch.cuda.device(self.device):
             check(self.lib.yg_get_state(self._h, C.byref(st), self._stream()))
         c = self.counters()
@@ -208,7 +209,7 @@ class ChainEnsemble:
     def load_state(self, r):
         st = YgState()
         keep = {k: r[k].to(self.device).contiguous() for k in
-                ('theta', 'logpost', 'n_accept', 'w_mean', 'w_m2', 'prop_L') if k in r}
+                ('theta', 'logpost', 'n_accept', 'w_mean', 'w_m2', 'prop_L', 'am_mean', 'am_m2') if k in r}
         st.theta_dev, st.logpost_dev = keep['theta'].data_ptr(), keep['logpost'].data_ptr()
         if 'n_accept' in keep:
             st.n_accept_dev = keep['n_accept'].data_ptr()
@@ -216,6 +217,8 @@ class ChainEnsemble:
             st.w_mean_dev, st.w_m2_dev = keep['w_mean'].data_ptr(), keep['w_m2'].data_ptr()
         if 'prop_L' in keep and self.cfg.adaptive:
             st.prop_L_dev = keep['prop_L'].data_ptr()
+        if 'am_mean' in keep and 'am_m2' in keep and self.cfg.adaptive:
+            st.am_mean_dev, st.am_m2_dev = keep['am_mean'].data_ptr(), keep['am_m2'].data_ptr()
         with torch.cuda.device(self.device):
             check(self.lib.yg_load_state(self._h, C.byref(st), int(r.get('step_index', 0)),
                                          int(r.get('welford_n', 0)), self._stream()))

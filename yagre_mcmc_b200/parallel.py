@@ -57,15 +57,12 @@ def pooled_diagnostics(ensemble):
     return moments_from_stats(vec, ensemble.dim)
 
 
-def split_rhat(samples):
-    """Split-R-hat per coordinate from stored samples [N, d, n] of THIS rank (+ all ranks when
-    torch.distributed is initialised): every chain is cut in two halves (yg_split_moments), the
-    halves are treated as 2n chains of length N/2."""
-    from .ensemble import split_moments
-    hm, hv = split_moments(samples)                        # [2, d, n] each
-    half = samples.shape[0] // 2
-    d = samples.shape[1]
-    stats = torch.stack([torch.full((d,), float(2 * samples.shape[2]), dtype=torch.float64, device=samples.device),
+def split_rhat_from_moments(hm, hv, half):
+    """Split-R-hat per coordinate from per-chain half moments hm, hv [2, d, n] (torch tensors on any
+    device) of THIS rank; all-reduced over ranks when torch.distributed is initialised.  The two
+    halves of every chain are treated as 2n chains of length `half`."""
+    d, n = hm.shape[1], hm.shape[2]
+    stats = torch.stack([torch.full((d,), float(2 * n), dtype=torch.float64, device=hm.device),
                          hm.sum(dim=(0, 2)), (hm * hm).sum(dim=(0, 2)), hv.sum(dim=(0, 2))])
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -74,3 +71,11 @@ def split_rhat(samples):
     W = sv / m
     B_over_n = (s2 - s1 * s1 / m) / (m - 1.0)
     return np.sqrt(((half - 1.0) / half * W + B_over_n) / W)
+
+
+def split_rhat(samples):
+    """Split-R-hat per coordinate from stored samples [N, d, n] of THIS rank (+ all ranks when
+    torch.distributed is initialised): every chain is cut in two halves (yg_split_moments)."""
+    from .ensemble import split_moments
+    hm, hv = split_moments(samples)                        # [2, d, n] each
+    return split_rhat_from_moments(hm, hv, samples.shape[0] // 2)
