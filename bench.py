@@ -100,16 +100,17 @@ def cpu_chain_steps_per_s(meta, arrays, target_seconds, seed=11):
     of the same workload: chains x transitions grown until about target_seconds of work."""
     from oracle import cport
     pb = cport.Problem(meta, arrays)
-    threads = cport.num_threads()
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1: ask explicitly)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_chains, n_tr = max(8 * threads, 64), 20
     th0 = bp.lv_initial_states(n_chains)
     t = time.perf_counter()
-    cport.run_philox(pb, th0, seed, n_tr, store=False)
+    cport.run_philox(pb, th0, seed, n_tr, store=False, n_threads=threads)
     dt = time.perf_counter() - t
     rate = n_chains * n_tr / dt
-    n_tr = int(max(20, min(2000, target_seconds * rate / n_chains)))
+    n_tr = int(max(20, min(20000, target_seconds * rate / n_chains)))
     t = time.perf_counter()
-    r = cport.run_philox(pb, th0, seed, n_tr, store=False)
+    r = cport.run_philox(pb, th0, seed, n_tr, store=False, n_threads=threads)
     dt = time.perf_counter() - t
     return dict(value=n_chains * n_tr / dt, seconds=dt, threads=threads, chains=n_chains, transitions=n_tr,
                 accept=float(r["n_accept"].sum()) / (n_chains * n_tr))

@@ -1,4 +1,4 @@
-"""Dev tool: per-CTA phase timers of the LV kernel (library built with -DYG_TIMERS)."""
+"""Dev tool: per-warp phase timers of the LV kernel (library built with `make -C yagre_mcmc_b200/csrc timers`)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -6,25 +6,38 @@ from yagre_mcmc_b200 import _lib
 _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libyagre_b200_timers.so")
 import bench_problems as bp
 from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem
-meta, arrays = bp.lv_problem(True)
+two = os.environ.get("LEVELS", "2") == "2"
+Nc, Nf = int(os.environ.get("NC", 64)), int(os.environ.get("NF", 512))
+meta, arrays = bp.lv_problem(two, Nc=Nc, Nf=Nf)
 pb = LoweredProblem(meta, arrays)
 n_chains, S = 65536, 20
-for bps, thr, seg in [(1, 1024, 64), (1, 1024, 128), (4, 256, 64), (2, 512, 64)]:
+names = ["owners", "wait1", "noise", "eval", "wait2", "commit"]
+for bps, thr, seg in [(1, 1024, 128)]:
     ens = ChainEnsemble(pb, n_chains, seed=1, blocks_per_sm=bps, threads_per_block=thr, rk4_segment=seg)
     ens.set_state(bp.lv_initial_states(n_chains))
     ens.run(100, samples=False)
+    if os.environ.get("SKIP"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ens.run(21, samples=False); e1.record(); torch.cuda.synchronize()
+        t_full = e0.elapsed_time(e1)
+        e0.record(); ens.run(21, thin=7, samples=False); e1.record(); torch.cuda.synchronize()
+        t_skip = e0.elapsed_time(e1)
+        e0.record(); ens.run(21, thin=7, samples=False); e1.record(); torch.cuda.synchronize()
+        t_skip2 = e0.elapsed_time(e1)
+        print(f"21 transitions: full {t_full:.3f} ms, without integration {t_skip:.3f} / {t_skip2:.3f} ms -> {t_skip2 / t_full:.4f} of the launch")
     out = ens.run(S, samples=True)
     torch.cuda.synchronize()
-    grid = ens.last_launch()['grid']
-    t = out['samples'].view(torch.int64).flatten()[:8 * grid].cpu().numpy().reshape(grid, 8).astype(np.float64)
-    owner, coarse, fine, total, nc_, nf_ = [t[:, i] for i in range(6)]
-    # ideal FP64-pipe cycles per CTA if it had 1/bps of an SM: instr * 2 cycles / (4 SMSP) * bps share
-    warp_instr_c = nc_ * 10 * 64 * 30 / 32.0
-    warp_instr_f = nf_ * 10 * 512 * 30 / 32.0
-    ideal_c = warp_instr_c * 2 / 4 * bps
-    ideal_f = warp_instr_f * 2 / 4 * bps
-    print(f"bps={bps} thr={thr} seg={seg}: per CTA mean cycles total={total.mean():.3e} (min {total.min():.3e} max {total.max():.3e}) "
-          f"owner={owner.mean()/total.mean():.3f} coarse={coarse.mean()/total.mean():.3f} fine={fine.mean()/total.mean():.3f} | "
-          f"coarse eff={ideal_c.mean()/coarse.mean():.3f} fine eff={ideal_f.mean()/fine.mean():.3f} "
-          f"overall eff={(ideal_c+ideal_f).mean()/total.max():.3f}")
+    grid = ens.last_launch()["grid"]
+    nw = thr // 32
+    t = out["samples"].view(torch.int64).flatten()[:10 * nw * grid].cpu().numpy().reshape(grid, nw, 10).astype(np.float64)
+    total = t[:, :, 8]
+    print(f"bps={bps} thr={thr} seg={seg}: CTA total cycles mean {total.mean():.4e} min {total.min():.4e} max {total.max():.4e}")
+    for k, nm in enumerate(names):
+        f = t[:, :, k] / total
+        print(f"  {nm:7s} share of CTA time: mean over warps {f.mean():.4f}  warp0-13 {f[:, :14].mean():.4f}  warp14-31 {f[:, 14:].mean():.4f}  min {f.min():.4f} max {f.max():.4f}")
+    items_c, items_f = t[:, 0, 6], t[:, 0, 7]
+    if not two:
+        items_c, items_f = np.zeros_like(items_c), items_c
+    ideal = (items_c * Nc + items_f * Nf) * 30 / 32.0 * 2 / 4 * bps
+    print(f"  ideal FP64-pipe cycles / CTA total: mean {np.mean(ideal / total[:, 0]):.4f}; vs slowest CTA {ideal.mean() / total.max():.4f}")
     ens.close()

@@ -9,7 +9,7 @@ from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem, fp64_peak_tf
 n_chains = int(os.environ.get("NCH", 65536))
 S = int(os.environ.get("S", 40))
 two = os.environ.get("LEVELS", "2") == "2"
-meta, arrays = bp.lv_problem(two_level=two)
+meta, arrays = bp.lv_problem(two_level=two, Nc=int(os.environ.get('NC', 64)), Nf=int(os.environ.get('NF', 512)), J=int(os.environ.get('JJ', 3)))
 pb = LoweredProblem(meta, arrays)
 peak = fp64_peak_tflops(0, 30.0)
 print("fp64 DFMA peak TFLOP/s:", peak, flush=True)
@@ -18,7 +18,7 @@ configs = [tuple(int(x) for x in c.split("x")) for c in os.environ.get("CFGS", "
 for bps, thr, seg in configs:
     ens = ChainEnsemble(pb, n_chains, seed=1, blocks_per_sm=bps, threads_per_block=thr, rk4_segment=seg)
     ens.set_state(th0)
-    ens.run(100, samples=False)           # burn-in / warm-up
+    ens.run(int(os.environ.get('BURN', 100)), samples=False)           # burn-in / warm-up
     torch.cuda.synchronize()
     c0 = ens.counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

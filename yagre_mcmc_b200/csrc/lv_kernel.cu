@@ -26,7 +26,11 @@
 //     enough for 1024 resident threads/SM; several CTAs per SM sit in different
 //     phases, which hides the owners' phases and the tails of the item loops;
 //   * the problem blob (design points, observations, precisions) is staged once
-//     per CTA into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier).
+//     per CTA into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier);
+//   * proposal noise does not depend on the chain state (counter-based Philox), so
+//     it is produced INSIDE the evaluation phases, one sub-step ahead of its use:
+//     the integer Philox rounds of the warps that draw noise overlap the FP64-pipe
+//     work of the warps that are already integrating.
 #include "ensemble.h"
 #include "lv_model.cuh"
 #include <math_constants.h>
@@ -39,6 +43,15 @@ struct SmemLayout {
     // doubles per chain slot
     enum { TH0, TH1, LP0, LP1, S0, S1, LPS, P0, P1, BETA, DELTA, WM0, WM1, W00, W01, W10, W11, NDBL };
 };
+
+#ifdef YG_TIMERS
+YG_DEVFN long long yg_clk()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#endif
 
 YG_DEVFN uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,15 +113,20 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
     off += sizeof(double) * (size_t)nd_max * cmax;                         //   segments, indexed by item
     double *sy = reinterpret_cast<double *>(smem_raw + off);
     off += sizeof(double) * (size_t)nd_max * cmax;
+    double *nz = reinterpret_cast<double *>(smem_raw + off);               // [3][cmax] next z0, z1, uniform
+    off += sizeof(double) * 3 * cmax;
     unsigned long long *nacc = reinterpret_cast<unsigned long long *>(smem_raw + off);   // [cmax]
     off += sizeof(unsigned long long) * cmax;
     int *list0 = reinterpret_cast<int *>(smem_raw + off);                  // [2][cmax]
     off += sizeof(int) * 2 * cmax;
+    int *segdone = reinterpret_cast<int *>(smem_raw + off);                // [n_data * cmax] segments done per item
+    off += sizeof(int) * (size_t)nd_max * cmax;
     unsigned char *evald = smem_raw + off;                                 // [cmax]
     off += (cmax + 15) & ~15;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + off);
     int *nact = reinterpret_cast<int *>(mbar + 1);                         // [2]
     unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [4]
+    int *qhead = reinterpret_cast<int *>(mbar + 6);                        // work-queue head of the current phase
 
     tma_stage_blob(pb, a.problem, (uint32_t)((a.problem_bytes + 15u) & ~15u), mbar);
     if (tid < 4) blk_cnt[tid] = 0ull;
@@ -128,11 +146,14 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
 
     // ---- one phase of forward evaluations over the compacted list ---------------
     // Work unit = (item, segment): item = (active chain, design point), segment = `seg_len`
-    // consecutive RK4 steps.  Units are ordered segment-major and dealt to the threads in
-    // rounds of R = min(blockDim, nItems) units, so consecutive segments of one item always
-    // fall into different rounds (their state travels through sx/sy) and only the LAST round
-    // of a phase is partially filled -- the quantisation loss is < R / nUnits instead of
-    // < blockDim / nItems.
+    // consecutive RK4 steps.  Units are ordered segment-major and handed out 32 at a time from
+    // a shared-memory queue: a warp that finishes grabs the next batch, so there is NO barrier
+    // inside a phase (with barriers between rounds the warps of a sub-partition finished a
+    // round one after another and the FP64 pipe ran dry at the end of every round: 5-8 % of
+    // the phase, profiles/r01_summary.md).  A unit of segment s > 0 continues the state its
+    // predecessor left in sx/sy; the predecessor has a smaller queue index, so it was grabbed
+    // earlier and never waits on anything later: the spin on segdone[item] cannot deadlock.
+    // A batch never holds two segments of one item (batch size <= nItems).
     auto eval_phase = [&](const int lvl, const int cur, const double h, const double ha, const double hg) {
         const DevLevel &Lv = pb->lvl[lvl];
         const int na = nact[cur];
@@ -141,19 +162,24 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
         const int Nrk = Lv.rk4_steps;
         const int nSeg = (Nrk + seg_len - 1) / seg_len;
         const int nUnits = nItems * nSeg;
-        const int R = min(nthr, nItems);
+        const int batch = min(32, nItems);
         const int *lst = list0 + cur * cmax;
         const double *design = tail + Lv.design_off;
         const double *data = tail + Lv.data_off;
         const double P00 = Lv.noise_prec[0], P01 = Lv.noise_prec[1], P10 = Lv.noise_prec[2], P11 = Lv.noise_prec[3];
         const float inv_items = 1.0f / (float)nItems, inv_na = 1.0f / (float)na;
+        const int lane = tid & 31;
         if (tid == 0) {
             nact[cur ^ 1] = 0;
             blk_cnt[2 + lvl] += (unsigned long long)na;
         }
-        for (int u0 = 0; u0 < nUnits; u0 += R) {
-            const int u = u0 + tid;
-            if (tid < R && u < nUnits) {
+        for (;;) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(qhead, batch);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= nUnits) break;
+            u += lane;
+            if (lane < batch && u < nUnits) {
                 const int seg = fast_div(u, nItems, inv_items), it = u - seg * nItems;
                 const int n = fast_div(it, na, inv_na), ai = it - n * na;
                 const int c = lst[ai];
@@ -163,10 +189,21 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                 r.hd = h * CH(DELTA, c);
                 double x, y;
                 if (seg == 0) { x = design[2 * n]; y = design[2 * n + 1]; }
-                else { x = sx[it]; y = sy[it]; }
+                else {
+                    const volatile int *flag = segdone + it;
+                    while (*flag < seg) __nanosleep(32);
+                    __threadfence_block();
+                    x = sx[it]; y = sy[it];
+                }
+#ifdef YG_TIMERS
+                lv_integrate(r, a.thin == 7 ? 0 : min(seg_len, Nrk - seg * seg_len), x, y);   // thin == 7: overhead-only run
+#else
                 lv_integrate(r, min(seg_len, Nrk - seg * seg_len), x, y);
+#endif
                 if (seg + 1 < nSeg) {
                     sx[it] = x; sy[it] = y;
+                    __threadfence_block();
+                    *(volatile int *)(segdone + it) = seg + 1;
                 } else {
                     // non-finite forward output -> +inf (policy of the oracle's RK4 plugin)
                     x = isfinite(x) ? x : CUDART_INF;
@@ -180,7 +217,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                     q[n * cmax + c] = fma(r1, t1, r0 * t0);
                 }
             }
-            if (u0 + R < nUnits) __syncthreads();
+            __syncwarp();
         }
     };
 
@@ -194,25 +231,40 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
         return logL + log_prior(lvl, t0, t1);
     };
 
-    // noise access: injected arrays are indexed by (step, sub-step), never by call count
-    auto uniform_c = [&](int64_t n, int j, int64_t g, uint64_t gid, uint64_t step) {
-        const int64_t i = (n * J + j) * N + g;
-        if (a.noise_mode == YG_NOISE_INJECT) return a.u_c[i];
-        const double u = philox_uniform(a.seed, gid, step, (uint32_t)j);
-        if (a.noise_mode == YG_NOISE_RECORD) a.u_c[i] = u;
-        return u;
+    // noise: injected arrays are indexed by (step, sub-step), never by call count.  draw_z /
+    // draw_u fill the chain's slot of nz one sub-step ahead of its use, always from the thread
+    // that owns the chain (producer == consumer, no barrier needed).
+    auto draw_z = [&](int c, int64_t g, int64_t n, int j) {
+        const uint64_t gid = (uint64_t)(a.chain_offset + g);
+        const int64_t zi = ((n * J + j) * LV_D) * N + g;
+        double z0, z1;
+        if (a.noise_mode == YG_NOISE_INJECT) {
+            z0 = a.z[zi]; z1 = a.z[zi + N];
+        } else {
+            philox_normal_pair(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, 0u, z0, z1);
+            if (a.noise_mode == YG_NOISE_RECORD) { a.z[zi] = z0; a.z[zi + N] = z1; }
+        }
+        nz[c] = z0; nz[cmax + c] = z1;
     };
-    auto uniform_f = [&](int64_t n, int64_t g, uint64_t gid, uint64_t step) {
-        const int64_t i = n * N + g;
-        if (a.noise_mode == YG_NOISE_INJECT) return a.u_f[i];
-        const double u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
-        if (a.noise_mode == YG_NOISE_RECORD) a.u_f[i] = u;
-        return u;
+    auto draw_u = [&](int c, int64_t g, int64_t n, int j, bool fine) {
+        const uint64_t gid = (uint64_t)(a.chain_offset + g);
+        double *arr = fine ? a.u_f : a.u_c;
+        const int64_t i = fine ? n * N + g : (n * J + j) * N + g;
+        double u;
+        if (a.noise_mode == YG_NOISE_INJECT) u = arr[i];
+        else {
+            u = philox_uniform(a.seed, gid, (uint64_t)(a.step0 + n), fine ? YG_SUB_FINE : (uint32_t)j);
+            if (a.noise_mode == YG_NOISE_RECORD) arr[i] = u;
+        }
+        nz[2 * cmax + c] = u;
     };
 
 #ifdef YG_TIMERS
+    // per-warp phase timers (dev build only): [0] owners' work [1] wait at the barrier after it
+    // [2] noise draws [3] evaluation loop [4] wait at the trailing barrier [5] commit
+    // [6] coarse items (tid 0) [7] fine items (tid 0)
     long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long dbg_last = clock64();
+    long long dbg_last = yg_clk();
     const long long dbg_start = dbg_last;
 #endif
     int cur = 0;
@@ -233,11 +285,11 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
             CH(W10, c) = a.w_m2[2 * N + g];
             CH(W11, c) = a.w_m2[3 * N + g];
             nacc[c] = a.n_accept[g];
+            if (a.n_steps > 0) draw_z(c, g, 0, 0);
         }
         unsigned long long my_acc = 0ull;
 
         for (int64_t n = 0; n < a.n_steps; n++) {
-            const uint64_t step = (uint64_t)(a.step0 + n);
             const double wn = (double)(a.welford_n0 + n + 1);
             // Phases j = 0..J-1: decide sub-step j-1, propose sub-step j, evaluate level 0.
             // Two level only, phase j = J: decide sub-step J-1, evaluate level 1 where the
@@ -245,9 +297,10 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
             const int n_phases = TWO_LEVEL ? J + 1 : 1;
             for (int j = 0; j < n_phases; j++) {
                 // =============== owners' phase ===================================
+                if (tid == 0) *qhead = 0;
+                if (pb->lvl[(TWO_LEVEL && j == J) ? 1 : 0].rk4_steps > seg_len)
+                    for (int i = tid; i < C * nd_max; i += nthr) segdone[i] = 0;
                 for (int c = tid; c < C; c += nthr) {
-                    const int64_t g = cb + c;
-                    const uint64_t gid = (uint64_t)(a.chain_offset + g);
                     double s0, s1, lps;
                     if (j == 0) {
                         // FullDiagnostics: Welford of the pre-transition state
@@ -266,7 +319,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                         if (evald[c]) {
                             const double p0 = CH(P0, c), p1 = CH(P1, c);
                             const double lpp = log_post_from_q(0, c, p0, p1);
-                            if (accept_rule(lpp - lps, uniform_c(n, j - 1, g, gid, step))) {
+                            if (accept_rule(lpp - lps, nz[2 * cmax + c])) {      // u_c(n, j-1)
                                 s0 = p0; s1 = p1; lps = lpp;
                             }
                         }
@@ -274,14 +327,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                     CH(S0, c) = s0; CH(S1, c) = s1; CH(LPS, c) = lps;
                     if (j < J) {
                         // propose sub-step j: p = s + L z  (gaussian.py:61-66), unfused like numpy
-                        double z0, z1;
-                        const int64_t zi = ((n * J + j) * LV_D) * N + g;
-                        if (a.noise_mode == YG_NOISE_INJECT) {
-                            z0 = a.z[zi]; z1 = a.z[zi + N];
-                        } else {
-                            philox_normal_pair(a.seed, gid, step, (uint32_t)j, 0u, z0, z1);
-                            if (a.noise_mode == YG_NOISE_RECORD) { a.z[zi] = z0; a.z[zi + N] = z1; }
-                        }
+                        const double z0 = nz[c], z1 = nz[cmax + c];          // z(n, j)
                         const double p0 = __dadd_rn(s0, __dmul_rn(L00, z0));
                         const double lz1 = (L10 != 0.0) ? __dadd_rn(__dmul_rn(L10, z0), __dmul_rn(L11, z1))
                                                         : __dmul_rn(L11, z1);
@@ -307,26 +353,49 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                         }
                     }
                 }
+#ifdef YG_TIMERS
+                const long long dbg_own = yg_clk();
+                dbg_t[0] += dbg_own - dbg_last;
+#endif
                 __syncthreads();
                 // =============== forward evaluations =============================
 #ifdef YG_TIMERS
-                const long long tA = clock64();
-                if (tid == 0) { dbg_t[0] += tA - dbg_last; dbg_t[4 + ((TWO_LEVEL && j == J) ? 1 : 0)] += nact[cur]; }
+                const long long tA = yg_clk();
+                dbg_t[1] += tA - dbg_own;
+                if (tid == 0) dbg_t[6 + ((TWO_LEVEL && j == J) ? 1 : 0)] += nact[cur] * pb->lvl[(TWO_LEVEL && j == J) ? 1 : 0].n_data;
+#endif
+                // noise one sub-step ahead: the uniform that decides the proposals being evaluated
+                // now, and the normals of the next proposal
+                {
+                    const bool last = (j == n_phases - 1);
+                    for (int c = tid; c < C; c += nthr) {
+                        const int64_t g = cb + c;
+                        draw_u(c, g, n, j, last);
+                        if (!last) { if (j + 1 < J) draw_z(c, g, n, j + 1); }
+                        else if (n + 1 < a.n_steps) draw_z(c, g, n + 1, 0);
+                    }
+                }
+#ifdef YG_TIMERS
+                const long long dbg_nz = yg_clk();
+                dbg_t[2] += dbg_nz - tA;
 #endif
                 // two inlined copies so that h, h*alpha, h*gamma are constant-bank operands
                 if (TWO_LEVEL && j == J) eval_phase(1, cur, a.lv_h[1], a.lv_ha[1], a.lv_hg[1]);
                 else eval_phase(0, cur, a.lv_h[0], a.lv_ha[0], a.lv_hg[0]);
+#ifdef YG_TIMERS
+                const long long dbg_ev = yg_clk();
+                dbg_t[3] += dbg_ev - dbg_nz;
+#endif
                 __syncthreads();
 #ifdef YG_TIMERS
-                dbg_last = clock64();
-                if (tid == 0) dbg_t[1 + ((TWO_LEVEL && j == J) ? 1 : 0)] += dbg_last - tA;
+                dbg_last = yg_clk();
+                dbg_t[4] += dbg_last - dbg_ev;
 #endif
                 cur ^= 1;
             }
             // =============== commit the transition ===============================
             for (int c = tid; c < C; c += nthr) {
                 const int64_t g = cb + c;
-                const uint64_t gid = (uint64_t)(a.chain_offset + g);
                 bool accepted = false;
                 if (evald[c]) {
                     if (TWO_LEVEL) {
@@ -334,7 +403,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                         const double lpf_s = log_post_from_q(1, c, s0, s1);
                         // mlda.py:148-152: pi_f(p) + pi_c(s) - pi_c(p) - pi_f(s), left to right
                         const double delta = lpf_s + CH(LP0, c) - CH(LPS, c) - CH(LP1, c);
-                        if (accept_rule(delta, uniform_f(n, g, gid, step))) {
+                        if (accept_rule(delta, nz[2 * cmax + c])) {                  // u_f(n)
                             CH(TH0, c) = s0; CH(TH1, c) = s1;
                             CH(LP0, c) = CH(LPS, c); CH(LP1, c) = lpf_s;
                             accepted = true;
@@ -342,7 +411,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                     } else {
                         const double p0 = CH(P0, c), p1 = CH(P1, c);
                         const double lpp = log_post_from_q(0, c, p0, p1);
-                        if (accept_rule(lpp - CH(LP0, c), uniform_f(n, g, gid, step))) {
+                        if (accept_rule(lpp - CH(LP0, c), nz[2 * cmax + c])) {       // u_f(n)
                             CH(TH0, c) = p0; CH(TH1, c) = p1; CH(LP0, c) = lpp;
                             accepted = true;
                         }
@@ -362,6 +431,9 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                     }
                 }
             }
+#ifdef YG_TIMERS
+            { const long long t = yg_clk(); dbg_t[5] += t - dbg_last; dbg_last = t; }
+#endif
             // the next owners' phase touches only the owner's own slots and list `cur`,
             // whose counter was zeroed during the last evaluation phase: no barrier needed
         }
@@ -386,10 +458,11 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
     }
     __syncthreads();
 #ifdef YG_TIMERS
-    if (tid == 0 && a.lp_out == nullptr && a.samples != nullptr) {   // debug: timers into the samples buffer
-        long long *o = reinterpret_cast<long long *>(a.samples) + 8 * blockIdx.x;
-        o[0] = dbg_t[0]; o[1] = dbg_t[1]; o[2] = dbg_t[2]; o[3] = clock64() - dbg_start;
-        o[4] = dbg_t[4]; o[5] = dbg_t[5]; o[6] = 0; o[7] = 0;
+    if ((tid & 31) == 0 && a.lp_out == nullptr && a.samples != nullptr) {   // debug: timers into the samples buffer
+        long long *o = reinterpret_cast<long long *>(a.samples) + 10 * (32 * blockIdx.x + (tid >> 5));
+        for (int k = 0; k < 8; k++) o[k] = dbg_t[k];
+        o[8] = yg_clk() - dbg_start;
+        o[9] = 0;
     }
 #endif
     if (tid < 4 && blk_cnt[tid]) atomicAdd(&a.counters[tid], blk_cnt[tid]);
@@ -401,10 +474,12 @@ size_t lv_smem_bytes(const yg_ensemble *e, int cmax, int nd_max)
     size_t off = (e->h_problem.size() + 15u) & ~size_t(15);
     off += sizeof(double) * SmemLayout::NDBL * cmax;
     off += sizeof(double) * (size_t)nd_max * cmax * 3;     // q, sx, sy
+    off += sizeof(double) * 3 * cmax;                      // nz
     off += sizeof(unsigned long long) * cmax;
     off += sizeof(int) * 2 * cmax;
+    off += sizeof(int) * (size_t)nd_max * cmax;           // segdone
     off += (cmax + 15) & ~15;
-    off += 8 + 8 + 32;
+    off += 8 + 8 + 32 + 8;
     return (off + 15) & ~size_t(15);
 }
 
@@ -435,7 +510,7 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     int64_t share = (a.n_chains + grid - 1) / grid;
     const size_t budget = (size_t)(220 * 1024) / bps;
     const size_t fixed = lv_smem_bytes(e, 0, nd_max);
-    const size_t per_chain = sizeof(double) * (SmemLayout::NDBL + 3 * nd_max) + 8 + 8 + 1;
+    const size_t per_chain = sizeof(double) * (SmemLayout::NDBL + 3 * nd_max + 3) + 4 * nd_max + 8 + 8 + 1;
     int64_t cap = fixed < budget ? (int64_t)((budget - fixed) / per_chain) : 0;
     if (cap < 1) {
         yg_set_error("problem blob too large for shared memory (%zu bytes)", fixed);
