@@ -15,7 +15,9 @@ peak = fp64_peak_tflops(0, 30.0)
 print("fp64 DFMA peak TFLOP/s:", peak, flush=True)
 th0 = bp.lv_initial_states(n_chains)
 configs = [tuple(int(x) for x in c.split("x")) for c in os.environ.get("CFGS", "4x256x32,4x256x16,4x256x64,2x512x32,2x512x16,2x256x32,3x256x32,8x128x32,1x512x16,4x256x8,3x320x32").split(",")]
-for bps, thr, seg in configs:
+for cfg_ in configs:
+    bps, thr, seg = cfg_[:3]
+    grp = cfg_[3] if len(cfg_) > 3 else 0
     ens = ChainEnsemble(pb, n_chains, seed=1, blocks_per_sm=bps, threads_per_block=thr, rk4_segment=seg)
     ens.set_state(th0)
     ens.run(int(os.environ.get('BURN', 100)), samples=False)           # burn-in / warm-up
@@ -33,7 +35,7 @@ for bps, thr, seg in configs:
     flops = bp.lv_flops_per_eval(nd, meta['Nc']) * ce + bp.lv_flops_per_eval(nd, meta['Nf']) * fe if two else bp.lv_flops_per_eval(nd, meta['Nf']) * fe
     steps = n_chains * S * 3
     acc = (c1['accepted'] - c0['accepted']) / steps
-    print(json.dumps(dict(bps=bps, thr=thr, seg=seg, launch=ens.last_launch(), ms=ms, steps_per_s=steps / ms * 1e3,
-                          tflops=flops / ms * 1e-9, frac=flops / ms * 1e-9 / peak, acc=acc,
+    print(json.dumps(dict(bps=bps, thr=thr, seg=seg, grp=grp, frac=round(flops / ms * 1e-9 / peak, 4), launch=ens.last_launch(), ms=ms, steps_per_s=steps / ms * 1e3,
+                          tflops=flops / ms * 1e-9, acc=acc,
                           fine_frac=fe / steps, coarse_per_step=ce / steps)), flush=True)
     ens.close()

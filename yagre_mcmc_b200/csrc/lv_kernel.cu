@@ -86,6 +86,17 @@ YG_DEVFN void tma_stage_blob(void *dst, const void *src, uint32_t bytes, uint64_
 
 // u / d for 0 <= u < 2^24 via a float reciprocal and one correction step: two integer
 // divisions per work unit were a measurable share of the non-FP64 issue slots.
+// Appends to a shared-memory list with ONE atomic per converged group of lanes.
+YG_DEVFN void list_append(int *list, int *count, int value)
+{
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
 YG_DEVFN int fast_div(int u, int d, float inv)
 {
     int q = __float2int_rz(__int2float_rz(u) * inv);
@@ -95,8 +106,8 @@ YG_DEVFN int fast_div(int u, int d, float inv)
     return q;
 }
 
-template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const int cmax, const int seg_len)
+template <bool TWO_LEVEL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const int cmax, const int seg_len)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -227,7 +238,8 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
         return -0.5 * quad_form<2>(Lv.prior_prec, LV_D, x, 2);
     };
     auto log_post_from_q = [&](int lvl, int c, double t0, double t1) {
-        const double logL = -0.5 * np_pairwise_sum(q + c, pb->lvl[lvl].n_data, cmax);
+        const int nD = pb->lvl[lvl].n_data;
+        const double logL = -0.5 * (nD <= 128 ? np_sum_le128(q + c, nD, cmax) : np_pairwise_sum(q + c, nD, cmax));
         return logL + log_prior(lvl, t0, t1);
     };
 
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                         if (!eq) {
                             CH(BETA, c) = exp(p0);     // LotkaVolterraParameter.evaluate, testSetup.py:57-58
                             CH(DELTA, c) = exp(p1);
-                            list0[cur * cmax + atomicAdd(&nact[cur], 1)] = c;
+                            list_append(list0 + cur * cmax, &nact[cur], c);
                         }
                     } else {
                         // sub-chain finished: s is the MLDA proposal (mlda.py:106-110); a chain whose
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(1024, 1) lv_mh_kernel(const RunArgs a, const i
                         if (moved) {
                             CH(BETA, c) = exp(s0);
                             CH(DELTA, c) = exp(s1);
-                            list0[cur * cmax + atomicAdd(&nact[cur], 1)] = c;
+                            list_append(list0 + cur * cmax, &nact[cur], c);
                         }
                     }
                 }
@@ -524,7 +536,9 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
         args.lv_ha[l] = args.lv_h[l] * hp->lvl[l].alpha;
         args.lv_hg[l] = args.lv_h[l] * hp->lvl[l].gamma;
     }
-    auto kern = two ? lv_mh_kernel<true> : lv_mh_kernel<false>;
+    // <= 512 threads: up to 128 registers per thread (no spills in the owners' phases)
+    auto kern = threads <= 512 ? (two ? lv_mh_kernel<true, 512> : lv_mh_kernel<false, 512>)
+                               : (two ? lv_mh_kernel<true, 1024> : lv_mh_kernel<false, 1024>);
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int seg_len = e->cfg.rk4_segment > 0 ? e->cfg.rk4_segment : 128;
     kern<<<grid, threads, smem, st>>>(args, cmax, seg_len);
