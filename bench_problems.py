@@ -65,6 +65,17 @@ def lv_problem(two_level=True, Nc=64, Nf=512, J=3, n_data=10, T=10.0, seed=1112,
     return meta, arrays
 
 
+def lv_pcn_problem(step=0.004, prior_var=1.4, Nf=512, n_data=10):
+    """pCN on the C4 likelihood (chain/method/pcn.py; test/test_inference_mcmc_singleLevel.py:121-148):
+    prop_L is the prior's factor and the level's prior precision is zero (likelihood-only target)."""
+    meta, arrays = lv_problem(False, Nf=Nf, n_data=n_data)
+    arrays['prop_L'] = _iid_L(prior_var, 2)
+    arrays['L0_prior_prec'] = np.zeros((2, 2))
+    arrays['pcn_mean'] = np.zeros(2)
+    meta.update(proposal='pcn', pcn_step=step)
+    return meta, arrays
+
+
 def lv_initial_states(n_chains, seed=7, chain_offset=0):
     """theta0 = theta* + 0.05 N(0, I) per chain (the example's [-7, 2.8] is unusable with RK4).
     Keyed on the global chain id so a sharded run starts exactly like the single-GPU run."""

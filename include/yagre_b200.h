@@ -21,7 +21,7 @@
  *                            Gaussian targets: test/testSetup.py:15-44)
  *   yg_set_state             initialState of MetropolisHastings.run  chain/metropolisHastings.py:103-110
  *   yg_run                   the loop of MetropolisHastings.run :112-120 with
- *                            MRWProposal mrw.py:27-38, _accept_reject :55-73,
+ *                            MRWProposal mrw.py:27-38, PCNProposal pcn.py:23-35, _accept_reject :55-73,
  *                            MLDAProposal.generate_proposal mlda.py:100-110 and
  *                            MLDA._acceptance_probability mlda.py:146-154,
  *                            AdaptiveMRWProposal.set_state chain/adaptive.py:55-60
@@ -101,9 +101,18 @@ typedef struct yg_level {
     int32_t _pad;
 } yg_level;
 
+typedef enum yg_proposal { YG_PROPOSAL_MRW = 0, YG_PROPOSAL_PCN = 1 } yg_proposal;
+
 typedef struct yg_problem {
     const double *prop_L;       /* [d,d] lower-triangular proposal factor, p = s + L z */
     yg_level level[2];          /* level[n_levels-1] is the target, level[0] the surrogate */
+    /* YG_PROPOSAL_PCN (chain/method/pcn.py:9-57, single level): prop_L is the factor of the PRIOR
+     * covariance, p = sqrt(1 - 2h) s + sqrt(2h) (pcn_mean + L z); the target is the likelihood
+     * alone, i.e. the caller passes a zero prior_prec for the level. */
+    int32_t proposal;           /* yg_proposal */
+    int32_t _pad;
+    double pcn_step;            /* h in (0, 0.5] */
+    const double *pcn_mean;     /* [d] prior mean (the reference requires zeros, pcn.py:44-46); NULL = zeros */
 } yg_problem;
 
 typedef struct yg_config {

@@ -29,7 +29,9 @@ class YoProblem(C.Structure):
     _fields_ = [("model", C.c_int32), ("dim", C.c_int32), ("n_levels", C.c_int32), ("J", C.c_int32),
                 ("eq_mode", C.c_int32), ("_pad", C.c_int32), ("prop_L", _dp), ("level", YoLevel * 2),
                 ("adaptive", C.c_int32), ("am_refresh", C.c_int32), ("am_idle", C.c_int64),
-                ("am_collect", C.c_int64), ("am_eps", C.c_double), ("am_scale", C.c_double)]
+                ("am_collect", C.c_int64), ("am_eps", C.c_double), ("am_scale", C.c_double),
+                ("pcn", C.c_int32), ("_pad2", C.c_int32), ("pcn_a", C.c_double), ("pcn_b", C.c_double),
+                ("pcn_mean", _dp)]
 
 
 def build(force=False):
@@ -83,6 +85,13 @@ class Problem:
             pb.am_eps = float(adaptive.get('eps', 1e-4))
             sc = float(adaptive.get('scale', 0.0))
             pb.am_scale = sc if sc > 0 else 2.4 * 2.4 / int(meta['dim'])
+
+        if meta.get('proposal', 'mrw') == 'pcn':
+            import math
+            t = 2. * float(meta['pcn_step'])
+            pb.pcn, pb.pcn_a, pb.pcn_b = 1, math.sqrt(1. - t), math.sqrt(t)
+            self.keep['pcn_mean'] = _arr(arrays.get('pcn_mean', np.zeros(int(meta['dim']))))
+            pb.pcn_mean = _ptr(self.keep['pcn_mean'])
 
         def put(obj, field, key):
             if key in arrays:

@@ -371,6 +371,56 @@ def cases_lv():
 
 
 # --------------------------------------------------------------------------
+# preconditioned Crank-Nicolson (chain/method/pcn.py; used by
+# test/test_inference_mcmc_singleLevel.py:121-148 and example_inference_lotkaVolterra_singleLevel.py:73-76)
+# --------------------------------------------------------------------------
+
+def case_pcn(name, model, stepSize, nChains, nSteps, seed, theta0, priorKind, priorValue, note):
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, 2, zero_at=[(0, 6, 0)])
+    if model == 'lv':
+        p = lv_problem()
+        stateType = rh.LotkaVolterraParameter
+    else:
+        p = linear_problem()
+        stateType = rh.ParameterVector
+    traj, acc, lp = [], [], []
+    for c in range(nChains):
+        if model == 'lv':
+            _, lik, _ = lv_models(p)
+        else:
+            _, lik, _ = linear_models(p)
+        prior = rh.Gaussian(stateType(np.zeros(2)), rh.covariance_from_spec(priorKind, priorValue, 2))
+        inj = rh.NoiseInjector(z[c], None, u_f[c])
+        b = rh.PCNBuilder()
+        b.bayesModel = rh.BayesianRegressionModel(lik, prior)
+        b.stepSize = stepSize
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, stateType(theta0[c].copy()), nSteps, inj, False)
+        traj.append(t); acc.append(a)
+        lp.append(logpost_along(lik, stateType, t))          # the pCN target is the likelihood alone (pcn.py:52-57)
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal(priorKind, priorValue, 2), pcn_mean=np.zeros(2),
+                  theta0=theta0, z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc, logpost_L0=lp)
+    lvl = lv_level_arrays(p, p['Nf'], 'L0_') if model == 'lv' else linear_level_arrays(p, 'f', 'L0_')
+    lvl['L0_prior_mean'] = np.zeros(2)
+    lvl['L0_prior_prec'] = np.zeros((2, 2))                  # likelihood-only target
+    arrays.update(lvl)
+    meta = dict(model=model, dim=2, levels=1, J=1, eq='exact', proposal='pcn', pcn_step=stepSize, note=note)
+    save(name, meta, arrays)
+
+
+def cases_pcn():
+    p = lv_problem()
+    rng = Generator(Philox(9))
+    theta0 = p['truth'] + 0.05 * rng.standard_normal((3, 2))
+    case_pcn("pcn_lv", 'lv', 0.004, 3, 120, 909, theta0, 'iid', 1.4,
+             'pCN on the C4 likelihood (RK4 N=512), prior N(0, 1.4 I), step 0.004')
+    case_pcn("pcn_linear_dense", 'linear', 0.05, 3, 300, 910, np.tile([1.0, 0.3], (3, 1)), 'dense',
+             [[2.0, 0.6], [0.6, 1.0]], 'pCN on the C3 fine likelihood, dense centred Gaussian prior, step 0.05')
+
+
+# --------------------------------------------------------------------------
 # post-processing pins: IAT, Welford, dense covariance
 # --------------------------------------------------------------------------
 
@@ -432,3 +482,5 @@ if __name__ == "__main__":
         case_postprocessing()
     if want('lv'):
         cases_lv()
+    if want('pcn'):
+        cases_pcn()

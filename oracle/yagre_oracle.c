@@ -60,6 +60,11 @@ typedef struct yo_problem {
     int32_t adaptive, am_refresh;
     int64_t am_idle, am_collect;
     double am_eps, am_scale;
+    /* preconditioned Crank-Nicolson (chain/method/pcn.py:9-57): prop_L is the PRIOR's factor,
+     * p = sqrt(1-2h) s + sqrt(2h) (m + L z); the target is the likelihood alone */
+    int32_t pcn, _pad2;
+    double pcn_a, pcn_b;       /* sqrt(1 - 2h), sqrt(2h) */
+    const double *pcn_mean;    /* [d] prior mean (zeros: pcn.py:44-46) */
 } yo_problem;
 
 /* ---------------------------------------------------------------------- */
@@ -200,7 +205,13 @@ static void propose(const yo_problem *pb, const double *L, const double *s, cons
                 first = 0;
             }
         }
-        p[i] = s[i] + acc;
+        if (pb->pcn) {
+            /* pcn.py:30-35: xi = mean + L z (gaussian.py:63-66), sqrt(1-t)*state + sqrt(t)*xi */
+            double xi = (pb->pcn_mean ? pb->pcn_mean[i] : 0.0) + acc;
+            p[i] = pb->pcn_a * s[i] + pb->pcn_b * xi;
+        } else {
+            p[i] = s[i] + acc;
+        }
     }
 }
 

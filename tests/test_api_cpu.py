@@ -14,7 +14,7 @@ from yagre_mcmc_b200.statistics import (IIDCovarianceMatrix, DiagonalCovarianceM
                                         GaussianTargetDensity2d, GaussianTargetDensity1d)
 from yagre_mcmc_b200.statistics.interface import DensityInterface
 from yagre_mcmc_b200.utility import Hierarchy, SharedComponent
-from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder
+from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder
 from yagre_mcmc_b200.chain.target import UnnormalisedPosterior
 from yagre_mcmc_b200.chain.lowering import lower_problem
 from yagre_mcmc_b200.parallel import shard_range, moments_from_stats
@@ -47,6 +47,27 @@ def test_builder_validation_messages():
     a = AMBuilder()
     with pytest.raises(ValueError, match="Regularisation parameter must be non-negative"):
         a.regularisationParameter = -1.0
+
+
+def test_pcn_builder_validation():
+    """reference chain/method/pcn.py:42-46,80-88."""
+    b = PCNBuilder()
+    with pytest.raises(ValueError, match="Step size not set in PCN"):
+        b.build_method()
+    b.stepSize = 0.01
+    b.explicitTarget = GaussianTargetDensity2d(ParameterVector(np.zeros(2)), np.eye(2))
+    with pytest.raises(RuntimeError, match="only defined in relation to a Bayesian model"):
+        b.build_method()
+    lik = AdditiveGaussianNoiseLikelihood(Data(np.zeros((2, 2))), ForwardModel(LinearModelSolver(np.eye(2), np.zeros(2))),
+                                          CentredGaussianNoise(IIDCovarianceMatrix(2, 1.)))
+    b2 = PCNBuilder()
+    b2.stepSize = 0.01
+    b2.bayesModel = BayesianRegressionModel(lik, Gaussian(ParameterVector(np.array([0.1, 0.])), IIDCovarianceMatrix(2, 1.)))
+    with pytest.raises(ValueError, match="requires centred prior"):
+        b2.build_method()
+    b2.stepSize = 0.7
+    with pytest.raises(AssertionError):
+        b2.build_method()
 
 
 def lv_objects():

@@ -13,7 +13,7 @@ from yagre_mcmc_b200.statistics import (IIDCovarianceMatrix, DiagonalCovarianceM
                                         BayesianRegressionModel, BayesianRegressionModelHierarchy,
                                         GaussianTargetDensity2d, GaussianTargetDensity1d)
 from yagre_mcmc_b200.utility import Hierarchy, SharedComponent
-from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder
+from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder
 from yagre_mcmc_b200.chain.diagnostics import DummyDiagnostics, AcceptanceRateDiagnostics, FullDiagnostics
 from yagre_mcmc_b200.postprocessing.autocorrelation import integrated_autocorrelation, effective_sample_size
 
@@ -185,6 +185,31 @@ def test_lv_single_level_mrw_through_builder():
         assert states.shape == (200, 128, 2) and np.all(np.isfinite(states))
         assert 0.05 < mc.diagnostics.global_acceptance_rate() < 0.95
         assert np.all(np.abs(states[100:].reshape(-1, 2).mean(0) - bp.LV_TRUTH) < 0.15)
+
+
+def test_lv_pcn_through_builder():
+    """reference test/test_inference_mcmc_singleLevel.py:121-148 (pCN on the LV posterior)."""
+    meta, arr, hier, lik, prior = _lv_hierarchy()
+    b = PCNBuilder()
+    b.bayesModel = BayesianRegressionModel(lik[1], prior)
+    b.stepSize = 0.004
+    b.diagnostics = FullDiagnostics()
+    b.nChains, b.seed = 256, 17
+    mc = b.build_method()
+    mc.run(400, LotkaVolterraParameter(bp.LV_TRUTH), verbose=False)
+    states = np.asarray(mc.chain.trajectory)
+    assert states.shape == (400, 256, 2) and np.all(np.isfinite(states))
+    assert 0.1 < mc.diagnostics.global_acceptance_rate() < 0.9
+    assert np.all(np.abs(states[200:].reshape(-1, 2).mean(0) - bp.LV_TRUTH) < 0.1)
+    # the pCN target is the likelihood alone (pcn.py:52-57): evaluate_log has no prior term
+    th = bp.LV_TRUTH + 0.01
+    from yagre_mcmc_b200.chain.method import MRWBuilder as _M
+    m = _M()
+    m.bayesModel = BayesianRegressionModel(lik[1], prior)
+    m.proposalCovariance = IIDCovarianceMatrix(2, 0.1)
+    post = m.build_method().target.evaluate_log(LotkaVolterraParameter(th))
+    like = mc.target.evaluate_log(LotkaVolterraParameter(th))
+    assert abs((post - like) - (-0.5 * float(th @ th) / 1.4)) < 1e-9
 
 
 def test_linear_two_level_through_builders_matches_closed_form():

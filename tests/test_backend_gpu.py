@@ -35,6 +35,7 @@ CASES = {
     "linear_two_level": lambda: (bp.linear_problem(True), lambda n: np.zeros((n, 2)), 1000, 200),
     "linear_single_level": lambda: (bp.linear_problem(False), lambda n: np.zeros((n, 2)), 1000, 200),
     "gauss2d": lambda: (bp.gauss2d_problem(), lambda n: np.tile([-8.0, -7.0], (n, 1)), 1000, 300),
+    "lv_pcn": lambda: (bp.lv_pcn_problem(), lambda n: bp.lv_initial_states(n), 300, 30),
 }
 
 
@@ -175,6 +176,24 @@ def test_error_paths_follow_reference_exception_types():
     bad["prop_L"] = np.eye(9)
     with pytest.raises((ValueError, NotImplementedError)):
         ChainEnsemble(LoweredProblem(dict(meta, dim=9), bad), 16)
+
+
+def test_pcn_posterior_moments_match_mrw():
+    """pCN (likelihood-ratio acceptance, prior-preserving proposal) and MRW (posterior-ratio acceptance)
+    target the same posterior: 8,192 chains each on the C4 problem must agree in mean and covariance."""
+    nc = 8192
+    out = []
+    for meta, arrays in (bp.lv_pcn_problem(), bp.lv_problem(False)):
+        ens = _ens(meta, arrays, nc, seed=31)
+        ens.set_state(bp.lv_initial_states(nc))
+        ens.run(300, samples=False)
+        th = ens.state()["theta"].cpu().numpy()
+        out.append((th.mean(1), np.cov(th)))
+        c = ens.counters()
+        assert 0.05 < c["accepted"] / c["transitions"] < 0.8
+    se = np.sqrt(np.diag(out[1][1]) / nc)
+    assert np.all(np.abs(out[0][0] - out[1][0]) < 6 * se)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=0.1, atol=2e-5)
 
 
 def test_logpost_matches_oracle():

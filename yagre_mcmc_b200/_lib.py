@@ -17,6 +17,7 @@ YG_OK, YG_ERR_INVALID, YG_ERR_CUDA, YG_ERR_UNSUPPORTED, YG_ERR_ABI, YG_ERR_STATE
 MODEL_GAUSS, MODEL_LINEAR, MODEL_LV = 0, 1, 2
 EQ_EXACT, EQ_ISCLOSE = 0, 1
 NOISE_PHILOX, NOISE_INJECT, NOISE_RECORD = 0, 1, 2
+PROPOSAL_MRW, PROPOSAL_PCN = 0, 1
 
 _dp = C.POINTER(C.c_double)
 
@@ -35,7 +36,8 @@ class YgLevel(C.Structure):
 
 
 class YgProblem(C.Structure):
-    _fields_ = [("prop_L", _dp), ("level", YgLevel * 2)]
+    _fields_ = [("prop_L", _dp), ("level", YgLevel * 2),
+                ("proposal", C.c_int32), ("_pad", C.c_int32), ("pcn_step", C.c_double), ("pcn_mean", _dp)]
 
 
 class YgConfig(C.Structure):

@@ -16,7 +16,8 @@ def _lower_density(density):
     return 'gauss', density.device_target()          # raises NotImplementedError when not Gaussian
 
 
-def lower_problem(targets, proposalCov, subChainLength=None, equality='exact'):
+def lower_problem(targets, proposalCov, subChainLength=None, equality='exact', proposal='mrw', pcnStep=None,
+                  pcnMean=None):
     """targets: [target] (MRW) or [surrogate, target] (two-level delayed acceptance)."""
     if len(targets) not in (1, 2):
         raise NotImplementedError(
@@ -38,4 +39,9 @@ def lower_problem(targets, proposalCov, subChainLength=None, equality='exact'):
             raise ValueError(f"level {l}: parameter dimension {arrays[key].size} does not match the "
                              f"proposal covariance ({dim})")
     meta = dict(model=model, dim=dim, levels=len(targets), J=int(subChainLength or 1), eq=equality)
+    if proposal == 'pcn':
+        if len(targets) != 1:
+            raise NotImplementedError("pCN is a single-level method (chain/method/pcn.py)")
+        meta.update(proposal='pcn', pcn_step=float(pcnStep))
+        arrays['pcn_mean'] = np.zeros(dim) if pcnMean is None else np.asarray(pcnMean, dtype=np.float64)
     return LoweredProblem(meta, arrays)

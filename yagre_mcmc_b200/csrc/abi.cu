@@ -197,6 +197,20 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
         return YG_ERR_INVALID;
     }
     const int d = e->cfg.dim, nl = e->cfg.n_levels, model = e->cfg.model;
+    if (pb->proposal != YG_PROPOSAL_MRW && pb->proposal != YG_PROPOSAL_PCN) {
+        yg_set_error("unknown proposal kind %d", pb->proposal);
+        return YG_ERR_INVALID;
+    }
+    if (pb->proposal == YG_PROPOSAL_PCN) {
+        if (!(pb->pcn_step > 0.0 && pb->pcn_step <= 0.5)) {       // pcn.py:42
+            yg_set_error("pCN step size must lie in (0, 0.5], got %g", pb->pcn_step);
+            return YG_ERR_INVALID;
+        }
+        if (nl != 1 || e->cfg.adaptive) {
+            yg_set_error("pCN is a single-level, non-adaptive method (chain/method/pcn.py)");
+            return YG_ERR_UNSUPPORTED;
+        }
+    }
     // tail: per level data + design
     size_t tail_len = 0;
     for (int l = 0; l < nl; l++) {
@@ -237,6 +251,13 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
     h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
     h->eq_mode = e->cfg.eq_mode;
     h->tail_len = (int32_t)tail_len;
+    h->proposal = pb->proposal;
+    if (pb->proposal == YG_PROPOSAL_PCN) {
+        const double t = 2.0 * pb->pcn_step;                      // pcn.py:30
+        h->pcn_a = sqrt(1.0 - t);
+        h->pcn_b = sqrt(t);
+        if (pb->pcn_mean) copy_mat(h->pcn_mean, pb->pcn_mean, 1, d);
+    }
     copy_mat(h->prop_L, pb->prop_L, d, d);
     for (int i = 0; i < d; i++)
         for (int j = i + 1; j < d; j++)

@@ -34,7 +34,10 @@ struct DevLevel {
 
 struct DevProblemHeader {
     int32_t model, dim, n_levels, J, eq_mode, tail_len;
-    int32_t _pad[2];
+    int32_t proposal;          // yg_proposal
+    int32_t _pad;
+    double pcn_a, pcn_b;       // sqrt(1 - 2h), sqrt(2h)   (pcn.py:30-35)
+    double pcn_mean[YG_MAX_DIM];
     double prop_L[YG_MAX_DIM * YG_MAX_DIM];
     DevLevel lvl[2];
     // followed by double tail[tail_len]: per level data[n_data*data_dim], design[n_data*2]

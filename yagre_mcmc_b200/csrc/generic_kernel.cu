@@ -8,7 +8,8 @@
 //   Gaussian targets     test/testSetup.py:15-44
 //   linear forward       exampleSetup.py:42-52 (A @ theta + b)
 //   likelihood / prior   statistics/likelihood.py:33-39,74-84, statistics/gaussian.py:19-24
-//   proposal             statistics/gaussian.py:61-66, statistics/covariance.py:51-52,84-86
+//   proposal             statistics/gaussian.py:61-66, statistics/covariance.py:51-52,84-86,
+//                        pCN: chain/method/pcn.py:23-35
 //   MRW / MLDA ratios    chain/method/mrw.py:51-57, chain/method/mlda.py:146-154
 //   step loop            chain/metropolisHastings.py:55-120
 //   adaptive interface   chain/adaptive.py:37-64 (update() before each proposal);
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
     const int n_lvl = TWO_LEVEL ? 2 : 1;
     const int64_t N = a.n_chains;
     const bool isclose_eq = pb->eq_mode == YG_EQ_ISCLOSE;
+    const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
 
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < N; g += (int64_t)gridDim.x * blockDim.x) {
@@ -230,7 +232,11 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
                         }
                     }
                 }
-                p[i] = (i < d) ? __dadd_rn(s[i], acc) : 0.0;
+                if (pcn)      // pcn.py:30-35: sqrt(1-t) * state + sqrt(t) * (mean + L z), unfused like numpy
+                    p[i] = (i < d) ? __dadd_rn(__dmul_rn(pb->pcn_a, s[i]), __dmul_rn(pb->pcn_b, __dadd_rn(pb->pcn_mean[i], acc)))
+                                   : 0.0;
+                else
+                    p[i] = (i < d) ? __dadd_rn(s[i], acc) : 0.0;
             }
         };
 

@@ -4,7 +4,7 @@
 //
 // Reference semantics restated (rkutri/yagre-mcmc):
 //   step loop            chain/metropolisHastings.py:103-120
-//   proposal             chain/method/mrw.py:27-38 -> statistics/gaussian.py:61-66
+//   proposal             chain/method/mrw.py:27-38 -> statistics/gaussian.py:61-66; pCN: chain/method/pcn.py:23-35
 //   equality skip        chain/metropolisHastings.py:60-61, parameter/vector.py:37-45
 //   likelihood           statistics/likelihood.py:33-39,74-84, statistics/covariance.py:19-22
 //   prior / posterior    statistics/gaussian.py:19-24, chain/target.py:19-22
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     const int J = TWO_LEVEL ? pb->J : 1;
     const int n_lvl = TWO_LEVEL ? 2 : 1;
     const double L00 = pb->prop_L[0], L10 = pb->prop_L[LV_D], L11 = pb->prop_L[LV_D + 1];
+    const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
 
 #define CH(field, c) chain[(SmemLayout::field) * cmax + (c)]
 
@@ -340,10 +341,17 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                     if (j < J) {
                         // propose sub-step j: p = s + L z  (gaussian.py:61-66), unfused like numpy
                         const double z0 = nz[c], z1 = nz[cmax + c];          // z(n, j)
-                        const double p0 = __dadd_rn(s0, __dmul_rn(L00, z0));
+                        const double lz0 = __dmul_rn(L00, z0);
                         const double lz1 = (L10 != 0.0) ? __dadd_rn(__dmul_rn(L10, z0), __dmul_rn(L11, z1))
                                                         : __dmul_rn(L11, z1);
-                        const double p1 = __dadd_rn(s1, lz1);
+                        double p0, p1;
+                        if (pcn) {    // pcn.py:30-35: sqrt(1-t) * state + sqrt(t) * (mean + L z)
+                            p0 = __dadd_rn(__dmul_rn(pb->pcn_a, s0), __dmul_rn(pb->pcn_b, __dadd_rn(pb->pcn_mean[0], lz0)));
+                            p1 = __dadd_rn(__dmul_rn(pb->pcn_a, s1), __dmul_rn(pb->pcn_b, __dadd_rn(pb->pcn_mean[1], lz1)));
+                        } else {
+                            p0 = __dadd_rn(s0, lz0);
+                            p1 = __dadd_rn(s1, lz1);
+                        }
                         const bool eq = (p0 == s0) && (p1 == s1);   // vector.py:37-45
                         evald[c] = !eq;
                         CH(P0, c) = p0; CH(P1, c) = p1;

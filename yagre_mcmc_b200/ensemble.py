@@ -27,7 +27,9 @@ class LoweredProblem:
     """The plain-array form of a (hierarchy of) Bayesian model(s) + proposal, i.e.
     what ChainBuilder.build_method() (reference chain/builder.py:72-83) boils down to.
 
-    meta:   model ('gauss'|'linear'|'lv'), dim, levels (1|2), J, eq ('exact'|'isclose')
+    meta:   model ('gauss'|'linear'|'lv'), dim, levels (1|2), J, eq ('exact'|'isclose'),
+            proposal ('mrw'|'pcn') and pcn_step for pCN (prop_L is then the prior's factor and the
+            level's prior_prec is zero: the pCN target is the likelihood alone, pcn.py:52-57)
     arrays: prop_L[d,d] and per level l: L{l}_g_mean/g_prec/g_logconst (gauss),
             L{l}_data/noise_prec/prior_mean/prior_prec (+ L{l}_G/b | L{l}_design/lv=[alpha,gamma,T,N])
     """
@@ -38,12 +40,16 @@ class LoweredProblem:
         self.levels = int(meta['levels'])
         self.J = int(meta.get('J', 1))
         self.eq = meta.get('eq', 'exact')
+        self.proposal = meta.get('proposal', 'mrw')
+        self.pcn_step = float(meta.get('pcn_step', 0.0))
+        if self.proposal not in ('mrw', 'pcn'):
+            raise NotImplementedError(f"proposal {self.proposal!r} has no device implementation")
         if self.model not in _MODEL:
             raise NotImplementedError(
                 f"model {self.model!r} has no device implementation; the backend accepts Gaussian targets, "
                 "linear models and the Lotka-Volterra RK4 model only (no CPU fallback)")
         self.arrays = {k: _f64(v) for k, v in arrays.items()
-                       if k == 'prop_L' or k.startswith('L0_') or k.startswith('L1_')}
+                       if k in ('prop_L', 'pcn_mean') or k.startswith('L0_') or k.startswith('L1_')}
         if 'prop_L' not in self.arrays:
             raise ValueError("Proposal Covariance not set")
 
@@ -51,6 +57,10 @@ class LoweredProblem:
         pb = YgProblem()
         a = self.arrays
         pb.prop_L = a['prop_L'].ctypes.data_as(_dp)
+        if self.proposal == 'pcn':
+            pb.proposal, pb.pcn_step = _lib.PROPOSAL_PCN, self.pcn_step
+            if 'pcn_mean' in a:
+                pb.pcn_mean = a['pcn_mean'].ctypes.data_as(_dp)
         for l in range(self.levels):
             lv = pb.level[l]
             pre = f"L{l}_"
