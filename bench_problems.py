@@ -117,6 +117,48 @@ def linear_posterior(level='f'):
     return cov @ rhs, cov
 
 
+def big_linear_problem(d=64, data_dim=256, n_data=1, two_level=False, J=2, seed=3, prop_var=None):
+    """GEMM-sized linear model (d = 64, dataDim = 256, nData = 1, G ~ N(0, 1/d), seed 3): served
+    by the DMMA kernel.  Diagonal noise / prior / proposal.  Two level: coarse = perturbed fine model."""
+    rng = Generator(Philox(seed))
+    G_f = rng.standard_normal((data_dim, d)) / np.sqrt(d)
+    b_f = 0.1 * rng.standard_normal(data_dim)
+    G_c = G_f + 0.05 * rng.standard_normal((data_dim, d)) / np.sqrt(d)
+    b_c = b_f + 0.02 * rng.standard_normal(data_dim)
+    truth = rng.standard_normal(d)
+    noise_var, prior_var = 0.05, 2.0
+    data = np.array([G_f @ truth + b_f + np.sqrt(noise_var) * rng.standard_normal(data_dim) for _ in range(n_data)])
+    if prop_var is None:
+        prop_var = 2.4 ** 2 / d * noise_var / max(n_data * data_dim / d, 1.0)      # ~ optimal RWM scaling
+
+    def level(G, b):
+        return dict(data=data, noise_prec=_diag_prec(noise_var, data_dim), prior_mean=np.zeros(d),
+                    prior_prec=_diag_prec(prior_var, d), G=G, b=b)
+    arrays = dict(prop_L=_iid_L(prop_var, d))
+    lv = [level(G_c, b_c), level(G_f, b_f)] if two_level else [level(G_f, b_f)]
+    for l, L in enumerate(lv):
+        arrays.update({f"L{l}_{k}": v for k, v in L.items()})
+    meta = dict(model='linear', dim=d, levels=2 if two_level else 1, J=J if two_level else 1, eq='exact',
+                truth=truth.tolist())
+    return meta, arrays
+
+
+def linear_gaussian_posterior(arrays, level):
+    """Closed-form Gaussian posterior (mean, covariance) of one level of a lowered linear problem."""
+    pre = f"L{level}_"
+    G, b, data = arrays[pre + 'G'], arrays[pre + 'b'], arrays[pre + 'data']
+    P0, m0, Pn = arrays[pre + 'prior_prec'], arrays[pre + 'prior_mean'], arrays[pre + 'noise_prec']
+    P = P0 + data.shape[0] * G.T @ Pn @ G
+    rhs = P0 @ m0 + G.T @ Pn @ (data - b).sum(axis=0)
+    cov = np.linalg.inv(P)
+    return cov @ rhs, cov
+
+
+def big_linear_flops_per_eval(d, data_dim):
+    """Algorithmic work of one forward evaluation of the linear model: the GEMV G theta (2 d dataDim)."""
+    return 2.0 * d * data_dim
+
+
 GAUSS2D_MEAN = np.array([1.0, 1.5])
 GAUSS2D_COV = np.array([[2.4, -0.5], [-0.5, 0.7]])
 

@@ -61,8 +61,13 @@ extern "C" {
 #endif
 
 #define YG_ABI_VERSION 2u
-#define YG_MAX_DIM 8           /* parameter dimension of the register-resident kernels */
+#define YG_MAX_DIM 8           /* parameter dimension of the one-chain-per-thread kernels */
 #define YG_MAX_DATA_DIM 8
+/* YG_MODEL_LINEAR beyond those sizes runs on the FP64 tensor path (DMMA GEMM, linear_dmma_kernel.cu):
+ * diagonal noise / prior precision and diagonal proposal factor, n_data <= 8, no adaptive Metropolis;
+ * Welford M2 is then diagonal only ([d, n_chains] instead of [d, d, n_chains]). */
+#define YG_BIG_MAX_DIM 64
+#define YG_BIG_MAX_DATA_DIM 256
 
 typedef enum yg_status {
     YG_OK = 0,
@@ -88,7 +93,7 @@ typedef struct yg_level {
     /* regression levels: log-likelihood + log-prior */
     int32_t n_data, data_dim;
     const double *data;         /* [n_data, data_dim] */
-    const double *noise_prec;   /* [data_dim, data_dim]; exact zeros are skipped */
+    const double *noise_prec;   /* [data_dim, data_dim]; exact zeros are skipped (large linear model: diagonal) */
     const double *prior_mean;   /* [d] */
     const double *prior_prec;   /* [d,d] */
     /* YG_MODEL_LINEAR: F = G theta + b */
@@ -210,6 +215,8 @@ int yg_split_moments(const double *samples_dev, int64_t n_samples, int32_t d, in
 
 /* Dependent-free DFMA chains on every SM for about `ms` milliseconds; returns TFLOP/s (FMA = 2). */
 int yg_fp64_peak(int32_t device, double ms, double *tflops_out);
+/* The same for the FP64 tensor path (independent m16n8k4 DMMA accumulator chains). */
+int yg_fp64_tensor_peak(int32_t device, double ms, double *tflops_out);
 
 /* Launch geometry and kernel count of the last yg_run (for bench.py's gpu_launches). */
 int yg_last_launch(yg_ensemble *e, int32_t *grid, int32_t *block, int32_t *smem_bytes, int64_t *launches);

@@ -271,6 +271,68 @@ def case_linear(twoLevel):
     save("mlda_linear" if twoLevel else "mrw_linear", meta, arrays)
 
 
+def big_linear_problem(d=16, dataDim=24, nData=3, seed=3):
+    """GEMM-sized linear model (SURVEY 8d 'GEMM-meaningful variant'): G ~ N(0, 1/d), coarse model = fine + perturbation."""
+    rng = Generator(Philox(seed))
+    G_f = rng.standard_normal((dataDim, d)) / np.sqrt(d)
+    b_f = 0.1 * rng.standard_normal(dataDim)
+    G_c = G_f + 0.05 * rng.standard_normal((dataDim, d)) / np.sqrt(d)
+    b_c = b_f + 0.02 * rng.standard_normal(dataDim)
+    truth = rng.standard_normal(d)
+    data = np.array([G_f @ truth + b_f + np.sqrt(0.05) * rng.standard_normal(dataDim) for _ in range(nData)])
+    return dict(G_f=G_f, b_f=b_f, G_c=G_c, b_c=b_c, data=data, noiseVar=0.05, priorMean=np.zeros(d) + 0.1,
+                priorVar=2.0, propVar=0.004, truth=truth, d=d, dataDim=dataDim)
+
+
+def case_big_linear(twoLevel):
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = big_linear_problem()
+    d, dd = p['d'], p['dataDim']
+    nChains, nSteps, J = 3, 150, (2 if twoLevel else 1)
+    rng = Generator(Philox(1300 + J))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, d, zero_at=[(0, 4, None)] if twoLevel else [(0, 4, 0)])
+    theta0 = p['truth'] + 0.05 * rng.standard_normal((nChains, d))
+    traj, acc, lpc, lpf = [], [], [], []
+    for c in range(nChains):
+        data = rh.Data(p['data'])
+        noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(dd, p['noiseVar']))
+        prior = rh.Gaussian(rh.ParameterVector(p['priorMean']), rh.IIDCovarianceMatrix(d, p['priorVar']))
+        likC = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_c'], p['b_c'])), noise)
+        likF = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_f'], p['b_f'])), noise)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        if twoLevel:
+            b = rh.MLDABuilder()
+            b.bayesModel = rh.BayesianRegressionModelHierarchy(rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+            b.baseProposalCovariance = rh.IIDCovarianceMatrix(d, p['propVar'])
+            b.subChainLengths = [J]
+        else:
+            b = rh.MRWBuilder()
+            b.bayesModel = rh.BayesianRegressionModel(likF, prior)
+            b.proposalCovariance = rh.IIDCovarianceMatrix(d, p['propVar'])
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(theta0[c].copy()), nSteps, inj, twoLevel)
+        traj.append(t); acc.append(a)
+        lpf.append(logpost_along(UnnormalisedPosterior(likF, prior), rh.ParameterVector, t))
+        lpc.append(logpost_along(UnnormalisedPosterior(likC, prior), rh.ParameterVector, t))
+        print(f"    big linear ({'two' if twoLevel else 'single'} level) chain {c}: acceptance {a.mean():.3f}")
+
+    def level(lvl, prefix):
+        return {prefix + 'data': p['data'], prefix + 'noise_prec': diag_precision(p['noiseVar'], dd),
+                prefix + 'prior_mean': p['priorMean'], prefix + 'prior_prec': diag_precision(p['priorVar'], d),
+                prefix + 'G': p['G_' + lvl], prefix + 'b': p['b_' + lvl]}
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], d), theta0=theta0, z=z, u_c=u_c, u_f=u_f,
+                  traj=traj, accepted=acc)
+    if twoLevel:
+        arrays.update(level('c', 'L0_')); arrays.update(level('f', 'L1_'))
+        arrays.update(logpost_L0=lpc, logpost_L1=lpf)
+    else:
+        arrays.update(level('f', 'L0_'))
+        arrays.update(logpost_L0=lpf)
+    meta = dict(model='linear', dim=d, levels=2 if twoLevel else 1, J=J, eq='exact',
+                note='GEMM-sized linear model d=16, dataDim=24, nData=3 (reference chain stack + exampleSetup-style A@theta+b)')
+    save("mlda_linear_big" if twoLevel else "mrw_linear_big", meta, arrays)
+
+
 # --------------------------------------------------------------------------
 # Lotka-Volterra (C4 / C5)
 # --------------------------------------------------------------------------
@@ -478,6 +540,9 @@ if __name__ == "__main__":
     if want('linear'):
         case_linear(False)
         case_linear(True)
+    if want('biglinear'):
+        case_big_linear(False)
+        case_big_linear(True)
     if want('post'):
         case_postprocessing()
     if want('lv'):

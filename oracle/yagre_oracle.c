@@ -31,7 +31,8 @@
 
 enum { YO_GAUSS = 0, YO_LINEAR = 1, YO_LV = 2 };
 enum { YO_EQ_EXACT = 0, YO_EQ_ISCLOSE = 1 };
-#define YO_MAX_DIM 16
+#define YO_MAX_DIM 64
+#define YO_MAX_DATA 256
 
 typedef struct yo_level {
     /* explicit Gaussian target: logp = -0.5 (t-m)' P (t-m) + logconst (testSetup.py:15-44) */
@@ -154,7 +155,7 @@ double yo_logpost(const yo_problem *pb, int lvl, const double *theta, int64_t *n
     }
     const int nD = L->n_data, dd = L->data_dim;
     double *q = (double *)malloc(sizeof(double) * (size_t)nD);
-    double r[YO_MAX_DIM], F[YO_MAX_DIM];
+    double r[YO_MAX_DATA], F[YO_MAX_DATA];
     if (n_evals) (*n_evals)++;
     if (pb->model == YO_LINEAR) {
         for (int k = 0; k < dd; k++) {               /* A @ theta + b  (exampleSetup.py:46) */
@@ -446,6 +447,7 @@ int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
 {
     const int d = pb->dim, J = pb->J;
     if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 2) return -1;
+    for (int l = 0; l < pb->n_levels; l++) if (pb->model != YO_GAUSS && pb->level[l].data_dim > YO_MAX_DATA) return -1;
     int64_t ev0 = 0, ev1 = 0;
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -482,6 +484,7 @@ int yo_run_philox(const yo_problem *pb, int64_t nc, int64_t chain_offset, uint64
 {
     const int d = pb->dim;
     if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 2) return -1;
+    for (int l = 0; l < pb->n_levels; l++) if (pb->model != YO_GAUSS && pb->level[l].data_dim > YO_MAX_DATA) return -1;
     if (thin < 1) thin = 1;
     const int64_t n_out = ns / thin;
     int64_t ev0 = 0, ev1 = 0;

@@ -8,7 +8,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 CHAIN_CASES = ["mrw_gauss1d", "mrw_gauss2d_iid", "mrw_gauss2d_diag", "mrw_gauss2d_dense",
                "mlda_gauss2d", "mrw_linear", "mlda_linear", "mrw_lv", "mlda_lv", "mlda_lv_nonfinite",
-               "pcn_lv", "pcn_linear_dense"]
+               "pcn_lv", "pcn_linear_dense", "mrw_linear_big", "mlda_linear_big"]
 
 
 def load(name):

@@ -43,6 +43,8 @@ def test_create_rejects_bad_config_without_touching_the_gpu():
     assert lib.yg_create(C.byref(cfg), C.byref(h)) == _lib.YG_ERR_ABI
     cfg.abi_version = _lib.YG_ABI_VERSION
     cfg.n_chains, cfg.dim, cfg.n_levels = 4, 99, 1
+    assert lib.yg_create(C.byref(cfg), C.byref(h)) == _lib.YG_ERR_UNSUPPORTED      # beyond every kernel's size
+    cfg.dim = 0
     assert lib.yg_create(C.byref(cfg), C.byref(h)) == _lib.YG_ERR_INVALID
     assert b"dim" in lib.yg_last_error()
     cfg.dim, cfg.n_levels = 2, 3            # >2 levels: reference quirk, out of scope

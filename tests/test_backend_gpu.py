@@ -36,6 +36,10 @@ CASES = {
     "linear_single_level": lambda: (bp.linear_problem(False), lambda n: np.zeros((n, 2)), 1000, 200),
     "gauss2d": lambda: (bp.gauss2d_problem(), lambda n: np.tile([-8.0, -7.0], (n, 1)), 1000, 300),
     "lv_pcn": lambda: (bp.lv_pcn_problem(), lambda n: bp.lv_initial_states(n), 300, 30),
+    # large linear model on the FP64 tensor path (DMMA): full size, ragged sizes, two level
+    "big_linear_64x256": lambda: (bp.big_linear_problem(64, 256, 1), lambda n: np.zeros((n, 64)), 200, 25),
+    "big_linear_ragged": lambda: (bp.big_linear_problem(23, 45, 3), lambda n: np.zeros((n, 23)), 77, 25),
+    "big_linear_two_level": lambda: (bp.big_linear_problem(32, 96, 2, two_level=True, J=3), lambda n: np.zeros((n, 32)), 150, 20),
 }
 
 
@@ -196,11 +200,42 @@ def test_pcn_posterior_moments_match_mrw():
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=0.1, atol=2e-5)
 
 
+def test_big_linear_posterior_moments_and_diagnostics():
+    """d = 64, dataDim = 256 on the DMMA kernel: the posterior is Gaussian in closed form."""
+    nc, d = 4096, 64
+    meta, arrays = bp.big_linear_problem(d, 256, 1)
+    mean, cov = bp.linear_gaussian_posterior(arrays, 0)
+    ens = _ens(meta, arrays, nc, seed=41)
+    ens.set_state(np.tile(mean, (nc, 1)))
+    ens.run(1500, samples=False)
+    out = ens.run(40, thin=40, samples=True, accepted=True)
+    th = out["samples"][-1].cpu().numpy()                       # [d, nc]
+    se = np.sqrt(np.diag(cov) / nc)
+    assert np.all(np.abs(th.mean(1) - mean) < 5 * se)
+    np.testing.assert_allclose(th.var(1, ddof=1), np.diag(cov), rtol=0.15)
+    c = ens.counters()
+    assert 0.1 < c["accepted"] / c["transitions"] < 0.5 and c["transitions"] == nc * 1540
+    st = ens.state()
+    assert tuple(st["w_m2"].shape) == (d, nc) and tuple(st["w_mean"].shape) == (d, nc)
+    assert torch.equal(st["theta"], out["samples"][-1])
+    assert st["welford_n"] == 1540 and torch.isfinite(st["w_m2"]).all()
+    with pytest.raises(NotImplementedError):
+        ens.pooled_stats()
+    # sizes beyond the kernel, or features it does not have, are refused loudly
+    with pytest.raises(NotImplementedError):
+        _ens(*bp.big_linear_problem(65, 64, 1), 16)
+    bad = dict(arrays)
+    bad["prop_L"] = np.linalg.cholesky(np.eye(d) + 0.01)
+    with pytest.raises(NotImplementedError):
+        _ens(meta, bad, 16)
+
+
 def test_logpost_matches_oracle():
     from oracle import cport
     rng = np.random.default_rng(0)
     for (meta, arrays), pts in [(bp.lv_problem(True), bp.LV_TRUTH + 0.3 * rng.standard_normal((64, 2))),
                                 (bp.linear_problem(True), rng.standard_normal((64, 2)) * 2),
+                                (bp.big_linear_problem(32, 96, 2, two_level=True), rng.standard_normal((64, 32))),
                                 (bp.gauss2d_problem(), rng.standard_normal((64, 2)) * 3)]:
         ens = _ens(meta, arrays, 4)
         pb = cport.Problem(meta, arrays)

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libyagre_b200.so")
 YG_ABI_VERSION = 2
 YG_MAX_DIM = 8
 YG_MAX_DATA_DIM = 8
+YG_BIG_MAX_DIM = 64
+YG_BIG_MAX_DATA_DIM = 256
 
 YG_OK, YG_ERR_INVALID, YG_ERR_CUDA, YG_ERR_UNSUPPORTED, YG_ERR_ABI, YG_ERR_STATE = 0, -1, -2, -3, -4, -5
 MODEL_GAUSS, MODEL_LINEAR, MODEL_LV = 0, 1, 2
@@ -86,6 +88,7 @@ SYMBOLS = {
     "yg_pooled_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "yg_split_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "yg_fp64_peak": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double)]),
+    "yg_fp64_tensor_peak": (C.c_int, [C.c_int32, C.c_double, C.POINTER(C.c_double)]),
     "yg_last_launch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int64)]),
 }

@@ -136,7 +136,8 @@ class MetropolisHastings:
         w_m2 = st['w_m2']
         stats = dict(n_accept=st['n_accept'].cpu().numpy(), transitions=st['step_index'],
                      welford_n=st['welford_n'], w_mean=st['w_mean'].t().cpu().numpy(),
-                     w_m2_diag=torch.stack([w_m2[i, i] for i in range(d)], dim=1).cpu().numpy(),
+                     w_m2_diag=(torch.stack([w_m2[i, i] for i in range(d)], dim=1) if w_m2.dim() == 3
+                                else w_m2.t()).cpu().numpy(),
                      squeeze=(self._nGlobal == 1))
         self._last = st
         self._diagnostics.process_ensemble(stats)

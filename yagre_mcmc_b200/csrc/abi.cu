@@ -1,6 +1,7 @@
 // abi.cu -- the extern "C" surface of libyagre_b200.so (include/yagre_b200.h).
 // Plain pointers and sizes only; no torch types, no exceptions across the boundary.
 #include "ensemble.h"
+#include "big_linear.h"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -90,6 +91,110 @@ __global__ void broadcast_L_kernel(const DevProblemHeader *pb, double *prop_L, i
         for (int k = 0; k < d * d; k++) prop_L[(int64_t)k * n + g] = pb->prop_L[k];
 }
 
+bool is_diagonal(const double *M, int n)
+{
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (i != j && M[i * n + j] != 0.0) return false;
+    return true;
+}
+
+// Large linear model: builds the DevBigHeader blob (big_linear.h) for linear_dmma_kernel.cu.
+int set_problem_big(yg_ensemble *e, const yg_problem *pb)
+{
+    const int d = e->cfg.dim, nl = e->cfg.n_levels;
+    if (pb->proposal != YG_PROPOSAL_MRW || e->cfg.adaptive || e->cfg.eq_mode != YG_EQ_EXACT) {
+        yg_set_error("large linear model: MRW / two-level delayed acceptance with exact equality only");
+        return YG_ERR_UNSUPPORTED;
+    }
+    if (!is_diagonal(pb->prop_L, d)) {
+        yg_set_error("large linear model: the proposal factor must be diagonal");
+        return YG_ERR_UNSUPPORTED;
+    }
+    const int kp = d <= 16 ? 16 : (d <= 32 ? 32 : 64), ks = kp + 4;
+    size_t tail_len = 0;
+    for (int l = 0; l < nl; l++) {
+        const yg_level &L = pb->level[l];
+        if (!L.data || !L.noise_prec || !L.prior_mean || !L.prior_prec || !L.G || !L.b || L.n_data < 1 ||
+            L.data_dim < 1) {
+            yg_set_error("level %d: linear level needs data, noise_prec, prior, G and b", l);
+            return YG_ERR_INVALID;
+        }
+        if (L.data_dim > YG_BIG_MAX_DATA_DIM || L.n_data > YG_BIG_MAX_ROWS) {
+            yg_set_error("level %d: large linear model is limited to data_dim <= %d and n_data <= %d", l,
+                         YG_BIG_MAX_DATA_DIM, YG_BIG_MAX_ROWS);
+            return YG_ERR_UNSUPPORTED;
+        }
+        if (!is_diagonal(L.noise_prec, L.data_dim) || !is_diagonal(L.prior_prec, d)) {
+            yg_set_error("level %d: large linear model needs diagonal noise and prior precision", l);
+            return YG_ERR_UNSUPPORTED;
+        }
+        const size_t np = (size_t)(L.data_dim + 7) & ~size_t(7);
+        tail_len += np * ks + np * 2 + 2 * (size_t)kp;
+    }
+    tail_len += kp;
+    tail_len = (tail_len + 1) & ~size_t(1);
+    if (sizeof(double) * tail_len > 216 * 1024) {
+        yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
+        return YG_ERR_UNSUPPORTED;
+    }
+    std::vector<char> blob(sizeof(DevBigHeader) + sizeof(double) * tail_len, 0);
+    DevBigHeader *h = reinterpret_cast<DevBigHeader *>(blob.data());
+    double *tail = reinterpret_cast<double *>(blob.data() + sizeof(DevBigHeader));
+    h->dim = d; h->kp = kp; h->ks = ks; h->n_levels = nl;
+    h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
+    h->tail_len = (int32_t)tail_len;
+    size_t off = 0;
+    for (int l = 0; l < nl; l++) {
+        const yg_level &L = pb->level[l];
+        BigLevel &B = h->lvl[l];
+        const int np = (L.data_dim + 7) & ~7;
+        B.n_data = L.n_data; B.data_dim = L.data_dim; B.np = np;
+        B.G_off = (int32_t)off;
+        for (int r = 0; r < L.data_dim; r++)
+            for (int k = 0; k < d; k++) tail[off + (size_t)r * ks + k] = L.G[(size_t)r * d + k];
+        off += (size_t)np * ks;
+        // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + sum_col P_col sum_rows (d - mean)^2
+        B.bd_off = (int32_t)off;
+        B.nw_off = (int32_t)(off + np);
+        double q_const = 0.0;
+        for (int r = 0; r < L.data_dim; r++) {
+            double mean = 0.0;
+            for (int i = 0; i < L.n_data; i++) mean += L.data[(size_t)i * L.data_dim + r];
+            mean /= (double)L.n_data;
+            double scatter = 0.0;
+            for (int i = 0; i < L.n_data; i++) {
+                const double dd = L.data[(size_t)i * L.data_dim + r] - mean;
+                scatter += dd * dd;
+            }
+            const double prec = L.noise_prec[(size_t)r * L.data_dim + r];
+            tail[off + r] = L.b[r] - mean;
+            tail[off + np + r] = (double)L.n_data * prec;
+            q_const += prec * scatter;
+        }
+        B.q_const = q_const;
+        off += 2 * (size_t)np;
+        B.pmean_off = (int32_t)off;
+        for (int k = 0; k < d; k++) tail[off + k] = L.prior_mean[k];
+        off += kp;
+        B.pprec_off = (int32_t)off;
+        for (int k = 0; k < d; k++) tail[off + k] = L.prior_prec[(size_t)k * d + k];
+        off += kp;
+    }
+    if (nl == 1) h->lvl[1] = h->lvl[0];
+    h->propL_off = (int32_t)off;
+    for (int k = 0; k < d; k++) tail[off + k] = pb->prop_L[(size_t)k * d + k];
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    if (e->d_problem) cudaFree(e->d_problem);
+    e->d_problem = nullptr;
+    YG_CUDA_CHECK(cudaMalloc((void **)&e->d_problem, blob.size()));
+    YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    e->h_problem.swap(blob);
+    e->problem_set = true;
+    e->big = true;
+    return YG_OK;
+}
+
 }  // namespace
 
 extern "C" const char *yg_last_error(void) { return g_err; }
@@ -106,9 +211,14 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
         yg_set_error("abi_version %u != library %u", cfg->abi_version, YG_ABI_VERSION);
         return YG_ERR_ABI;
     }
-    if (cfg->n_chains < 1 || cfg->dim < 1 || cfg->dim > YG_MAX_DIM) {
-        yg_set_error("n_chains=%lld dim=%d out of range (dim 1..%d)", (long long)cfg->n_chains, cfg->dim, YG_MAX_DIM);
-        return YG_ERR_INVALID;
+    const int max_dim = cfg->model == YG_MODEL_LINEAR ? YG_BIG_MAX_DIM : YG_MAX_DIM;
+    if (cfg->n_chains < 1 || cfg->dim < 1 || cfg->dim > max_dim) {
+        yg_set_error("n_chains=%lld dim=%d out of range (dim 1..%d)", (long long)cfg->n_chains, cfg->dim, max_dim);
+        return cfg->dim > max_dim ? YG_ERR_UNSUPPORTED : YG_ERR_INVALID;
+    }
+    if (cfg->dim > YG_MAX_DIM && cfg->adaptive) {
+        yg_set_error("adaptive Metropolis is limited to dim <= %d", YG_MAX_DIM);
+        return YG_ERR_UNSUPPORTED;
     }
     if (cfg->n_levels != 1 && cfg->n_levels != 2) {
         yg_set_error("n_levels=%d: only MRW (1) and two-level delayed acceptance (2) exist on the device",
@@ -152,9 +262,9 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
     const size_t n = (size_t)cfg->n_chains, d = (size_t)cfg->dim;
     int rc = YG_OK;
     if ((rc = dev_alloc(&e->theta, d * n)) || (rc = dev_alloc(&e->logpost, 2 * n)) ||
-        (rc = dev_alloc(&e->w_mean, d * n)) || (rc = dev_alloc(&e->w_m2, d * d * n)) ||
+        (rc = dev_alloc(&e->w_mean, d * n)) || (rc = dev_alloc(&e->w_m2, (cfg->dim > YG_MAX_DIM ? d : d * d) * n)) ||
         (rc = dev_alloc(&e->n_accept, n)) || (rc = dev_alloc(&e->counters, 8)) ||
-        (rc = dev_alloc(&e->pool_partials, (size_t)POOL_PARTS * (size_t)yg_pooled_len(cfg->dim)))) {
+        (rc = dev_alloc(&e->pool_partials, (size_t)POOL_PARTS * (size_t)yg_pooled_len(std::min(cfg->dim, YG_MAX_DIM))))) {
         yg_destroy(e);
         return rc;
     }
@@ -197,6 +307,12 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
         return YG_ERR_INVALID;
     }
     const int d = e->cfg.dim, nl = e->cfg.n_levels, model = e->cfg.model;
+    if (model == YG_MODEL_LINEAR) {
+        bool big = d > YG_MAX_DIM;
+        for (int l = 0; l < nl; l++) big = big || pb->level[l].data_dim > YG_MAX_DATA_DIM;
+        if (big) return set_problem_big(e, pb);
+    }
+    e->big = false;
     if (pb->proposal != YG_PROPOSAL_MRW && pb->proposal != YG_PROPOSAL_PCN) {
         yg_set_error("unknown proposal kind %d", pb->proposal);
         return YG_ERR_INVALID;
@@ -319,7 +435,7 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     YG_CUDA_CHECK(cudaMemcpyAsync(e->theta, theta0_dev, sizeof(double) * d * n, cudaMemcpyDeviceToDevice, st));
     YG_CUDA_CHECK(cudaMemsetAsync(e->w_mean, 0, sizeof(double) * d * n, st));
-    YG_CUDA_CHECK(cudaMemsetAsync(e->w_m2, 0, sizeof(double) * d * d * n, st));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->w_m2, 0, sizeof(double) * (d > YG_MAX_DIM ? d : d * d) * n, st));
     YG_CUDA_CHECK(cudaMemsetAsync(e->n_accept, 0, sizeof(unsigned long long) * n, st));
     YG_CUDA_CHECK(cudaMemsetAsync(e->counters, 0, sizeof(unsigned long long) * 8, st));
     if (e->cfg.adaptive) {
@@ -330,7 +446,8 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
         YG_CUDA_CHECK(cudaGetLastError());
     }
     for (int l = 0; l < e->cfg.n_levels; l++) {
-        rc = yg_launch_logpost(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st);
+        rc = e->big ? yg_launch_logpost_big(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st)
+                    : yg_launch_logpost(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st);
         if (rc) return rc;
     }
     e->step_index = 0;
@@ -378,8 +495,9 @@ extern "C" int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin, const yg_ou
         a.u_f = noise->u_f_dev;
     }
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    rc = (e->cfg.model == YG_MODEL_LV_RK4) ? yg_launch_lv(e, a, false, (cudaStream_t)stream)
-                                           : yg_launch_generic(e, a, false, (cudaStream_t)stream);
+    rc = e->big ? yg_launch_linear_big(e, a, (cudaStream_t)stream)
+         : (e->cfg.model == YG_MODEL_LV_RK4) ? yg_launch_lv(e, a, false, (cudaStream_t)stream)
+                                             : yg_launch_generic(e, a, false, (cudaStream_t)stream);
     if (rc) return rc;
     e->step_index += n_steps;
     e->welford_n += n_steps;
@@ -399,7 +517,7 @@ extern "C" int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream)
     if (dst->logpost_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->logpost_dev, e->logpost, 8 * nl * n, k, st));
     if (dst->n_accept_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->n_accept_dev, e->n_accept, 8 * n, k, st));
     if (dst->w_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->w_mean_dev, e->w_mean, 8 * d * n, k, st));
-    if (dst->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->w_m2_dev, e->w_m2, 8 * d * d * n, k, st));
+    if (dst->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->w_m2_dev, e->w_m2, 8 * (d > YG_MAX_DIM ? d : d * d) * n, k, st));
     if (dst->prop_L_dev) {
         if (!e->cfg.adaptive) {
             yg_set_error("prop_L_dev is per-chain state of adaptive ensembles only");
@@ -434,7 +552,7 @@ extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_i
     YG_CUDA_CHECK(cudaMemcpyAsync(e->logpost, src->logpost_dev, 8 * nl * n, k, st));
     if (src->n_accept_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->n_accept, src->n_accept_dev, 8 * n, k, st));
     if (src->w_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_mean, src->w_mean_dev, 8 * d * n, k, st));
-    if (src->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_m2, src->w_m2_dev, 8 * d * d * n, k, st));
+    if (src->w_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->w_m2, src->w_m2_dev, 8 * (d > YG_MAX_DIM ? d : d * d) * n, k, st));
     if (src->prop_L_dev && e->cfg.adaptive)
         YG_CUDA_CHECK(cudaMemcpyAsync(e->prop_L, src->prop_L_dev, 8 * d * d * n, k, st));
     if (src->am_mean_dev && e->cfg.adaptive)
@@ -475,7 +593,8 @@ extern "C" int yg_logpost(yg_ensemble *e, int32_t level, const double *theta_dev
         return YG_ERR_INVALID;
     }
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    return yg_launch_logpost(e, level, theta_dev, n, out_dev, (cudaStream_t)stream);
+    return e->big ? yg_launch_logpost_big(e, level, theta_dev, n, out_dev, (cudaStream_t)stream)
+                  : yg_launch_logpost(e, level, theta_dev, n, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int yg_pooled_stats(yg_ensemble *e, double *out_dev, void *stream)
@@ -483,6 +602,10 @@ extern "C" int yg_pooled_stats(yg_ensemble *e, double *out_dev, void *stream)
     int rc = check_handle(e, true, true);
     if (rc) return rc;
     if (!out_dev) return YG_ERR_INVALID;
+    if (e->cfg.dim > YG_MAX_DIM) {
+        yg_set_error("pooled statistics need the full second-moment matrix (dim <= %d)", YG_MAX_DIM);
+        return YG_ERR_UNSUPPORTED;
+    }
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     return yg_pooled_impl(e->w_mean, e->w_m2, e->n_accept, e->cfg.dim, e->cfg.n_chains, e->welford_n,
                           e->pool_partials, POOL_PARTS, out_dev, (cudaStream_t)stream);
@@ -496,4 +619,10 @@ extern "C" int yg_last_launch(yg_ensemble *e, int32_t *grid, int32_t *block, int
     if (smem_bytes) *smem_bytes = e->last_smem;
     if (launches) *launches = e->launches;
     return YG_OK;
+}
+
+extern "C" int yg_fp64_tensor_peak(int32_t device, double ms, double *tflops_out)
+{
+    if (!tflops_out) return YG_ERR_INVALID;
+    return yg_dmma_peak(device, ms, tflops_out);
 }

@@ -1,0 +1,29 @@
+// big_linear.h -- device problem blob of the large linear model (linear_dmma_kernel.cu):
+// d up to YG_BIG_MAX_DIM, data_dim up to YG_BIG_MAX_DATA_DIM, diagonal noise / prior / proposal.
+#pragma once
+#include <stdint.h>
+#include "../../include/yagre_b200.h"
+
+#define YG_BIG_MAX_ROWS 8         /* data rows (n_data) */
+
+struct BigLevel {
+    int32_t n_data, data_dim, np, _pad;             // np = data_dim rounded up to a multiple of 8
+    int32_t G_off, bd_off, nw_off, pmean_off;       // offsets (doubles) into the tail
+    int32_t pprec_off, _pad2[3];
+    double q_const, _pad3;                          // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
+};
+
+struct DevBigHeader {
+    int32_t dim, kp, ks, n_levels;                  // kp in {16, 32, 64} >= dim; ks = kp + 4 (row stride of G)
+    int32_t J, tail_len, propL_off, _pad;
+    BigLevel lvl[2];
+    // followed by double tail[tail_len]: per level G[np][ks], bd[np] = b - mean_rows(data),
+    // nw[np] = n_data * noise precision, pmean[kp], pprec[kp]; then propL[kp].  Padding is zero.
+    // sum_rows ||F - d_row||^2_P = sum_col nw_col (F_col - mean_col)^2 + q_const.
+};
+static_assert(sizeof(DevBigHeader) % 16 == 0, "header must keep 16-byte alignment");
+
+// Welford second moment of the large model is diagonal only (like the reference's
+// WelfordAccumulator, statistics/estimation.py:4-58): w_m2 is [d, n] when d > YG_MAX_DIM and the
+// diagonal of the [d, d, n] layout otherwise.
+__host__ __device__ inline int big_w2_index(int k, int d) { return d > YG_MAX_DIM ? k : k * d + k; }

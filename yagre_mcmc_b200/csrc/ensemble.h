@@ -42,6 +42,7 @@ struct yg_ensemble {
     yg_config cfg;
     int sm_count = 0;
     bool problem_set = false, state_set = false;
+    bool big = false;                  // large linear model: DevBigHeader blob, linear_dmma_kernel.cu
     std::vector<char> h_problem;
     DevProblemHeader *d_problem = nullptr;
     double *theta = nullptr, *logpost = nullptr, *w_mean = nullptr, *w_m2 = nullptr;
@@ -57,3 +58,6 @@ struct yg_ensemble {
 int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool init_only, cudaStream_t st);
 int yg_launch_generic(yg_ensemble *e, const RunArgs &a, bool init_only, cudaStream_t st);
 int yg_launch_logpost(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st);
+int yg_launch_linear_big(yg_ensemble *e, const RunArgs &a, cudaStream_t st);
+int yg_launch_logpost_big(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st);
+int yg_dmma_peak(int device, double ms, double *tflops_out);

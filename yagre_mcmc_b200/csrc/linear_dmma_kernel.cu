@@ -1,0 +1,448 @@
+// linear_dmma_kernel.cu -- Metropolis-Hastings over an ensemble of chains on the LINEAR model
+// F = G theta + b when the parameter / data dimensions are too large for one chain per thread
+// (d up to 64, data_dim up to 256): the forward model of a tile of chains is a dense FP64 GEMM
+// [chains x d] . [d x data_dim], issued on the FP64 tensor path (DMMA, mma.sync m16n8k4.f64),
+// with the Gaussian-misfit log-likelihood fused into the accumulator epilogue.
+//
+// Reference semantics restated (rkutri/yagre-mcmc):
+//   linear forward       exampleSetup.py:42-52 (A @ theta + b, broadcast against the data rows)
+//   likelihood / prior   statistics/likelihood.py:33-39,74-84, statistics/gaussian.py:19-24,
+//                        statistics/covariance.py:19-22,54-55 (diagonal precisions)
+//   proposal             statistics/gaussian.py:61-66 with a diagonal factor (covariance.py:51-52)
+//   MRW / MLDA ratios    chain/method/mrw.py:51-57, chain/method/mlda.py:100-110,146-154
+//   step loop            chain/metropolisHastings.py:55-120
+//   Welford diagnostics  chain/diagnostics.py:91-94, statistics/estimation.py:36-53 (diagonal M2)
+//
+// B200 mapping
+//   * persistent CTAs (one per SM), 8 warps; a warp owns a tile of 16 chains (the M extent of
+//     m16n8k4) for ALL n_steps.  The chain state lives in registers in A-fragment layout: lane
+//     (g = lane / 4, t = lane % 4) holds theta[row g and g+8][k = 4 i + t], so a proposal is
+//     already the A operand of the GEMM -- no shared-memory round trip for the chain state;
+//   * G of every level is staged once per CTA into shared memory (row stride = 4 mod 16 doubles:
+//     the B-fragment loads of a warp are bank-conflict free) and shared by the 8 warps; with 16
+//     chains per B fragment the shared-memory traffic is 1/2 of the DMMA issue time;
+//   * epilogue per 16x8 accumulator tile: + b, - data row, * noise precision, squared, summed
+//     per chain; a 4-lane butterfly finishes the row sums, so the four lanes of a chain hold
+//     bit-identical log-posteriors and take the same accept decision without further traffic;
+//   * Philox noise is keyed exactly like the one-chain-per-thread kernels, so results do not
+//     depend on which kernel serves a problem size.
+#include "ensemble.h"
+#include "big_linear.h"
+#include <math_constants.h>
+
+namespace {
+
+YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double b0)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
+        : "d"(a0), "d"(a1), "d"(b0));
+}
+
+YG_DEVFN double quad_sum(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+struct SmemLevel {
+    const double *G;        // [np][ks]
+    const double *bd;       // [np]   b - mean over the data rows (likelihood.py:74-75 broadcasts F against the rows)
+    const double *nw;       // [np]   n_data * noise precision (zero beyond data_dim)
+    const double *pmean;    // [kp]
+    const double *pprec;    // [kp]   (zero beyond dim)
+    double q_const;         // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
+    int np;
+};
+
+// log-posterior of the two chains (rows g, g+8) whose parameters are spread over the quad:
+// a[r][i] = theta_row_r[4 i + t].  Every lane of a quad returns the same two values.
+template <int KQ>
+YG_DEVFN void logpost_tile(const SmemLevel &L, const int ks, const double (&a)[2][KQ], const int g, const int t,
+                           double &lp_r0, double &lp_r1)
+{
+    // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + q_const  (exact identity;
+    // no cancellation: the row scatter is a precomputed constant)
+    double q0 = 0.0, q1 = 0.0;
+    for (int nb = 0; nb < L.np; nb += 8) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, a[0][i], a[1][i], Gb[4 * i]);
+        const int col = nb + 2 * t;
+        const double b0 = L.bd[col], b1 = L.bd[col + 1], w0 = L.nw[col], w1 = L.nw[col + 1];
+        const double e00 = c0 + b0, e01 = c1 + b1, e10 = c2 + b0, e11 = c3 + b1;     // A @ theta + b - mean(data)
+        q0 = fma(w1 * e01, e01, fma(w0 * e00, e00, q0));
+        q1 = fma(w1 * e11, e11, fma(w0 * e10, e10, q1));
+    }
+    const double s0 = quad_sum(q0) + L.q_const, s1 = quad_sum(q1) + L.q_const;
+    double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < KQ; i++) {
+        const double m = L.pmean[4 * i + t], w = L.pprec[4 * i + t];
+        const double x0 = a[0][i] - m, x1 = a[1][i] - m;
+        p0 = fma(w * x0, x0, p0);
+        p1 = fma(w * x1, x1, p1);
+    }
+    lp_r0 = -0.5 * s0 + (-0.5 * quad_sum(p0));
+    lp_r1 = -0.5 * s1 + (-0.5 * quad_sum(p1));
+}
+
+template <int KQ, bool TWO_LEVEL>
+__global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    // ---- stage the problem into shared memory -------------------------------------------------
+    const DevBigHeader H = *gh;
+    const double *gtail = reinterpret_cast<const double *>(gh + 1);
+    for (int i = tid; i < H.tail_len; i += blockDim.x) smem[i] = gtail[i];
+    __syncthreads();
+    SmemLevel Lv[2];
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        Lv[l].G = smem + H.lvl[l].G_off;
+        Lv[l].bd = smem + H.lvl[l].bd_off;
+        Lv[l].nw = smem + H.lvl[l].nw_off;
+        Lv[l].pmean = smem + H.lvl[l].pmean_off;
+        Lv[l].pprec = smem + H.lvl[l].pprec_off;
+        Lv[l].q_const = H.lvl[l].q_const;
+        Lv[l].np = H.lvl[l].np;
+    }
+    const double *propL = smem + H.propL_off;      // [kp] diagonal proposal factor (zero beyond dim)
+    const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
+    const int64_t N = a.n_chains;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+
+    const int64_t n_tiles = (N + 15) / 16;
+    for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+        // rows of this lane: chains gr[0], gr[1] (a row beyond n_chains is computed but never stored)
+        int64_t gr[2] = {tile * 16 + g, tile * 16 + g + 8};
+        bool live[2] = {gr[0] < N, gr[1] < N};
+        double th[2][KQ];
+        double lp0[2], lp1[2];
+        unsigned long long nacc[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int64_t gg = live[r] ? gr[r] : 0;
+#pragma unroll
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                const bool in = k < d;
+                th[r][i] = in ? a.theta[(int64_t)k * N + gg] : 0.0;
+            }
+            lp0[r] = a.logpost[gg];
+            lp1[r] = TWO_LEVEL ? a.logpost[N + gg] : 0.0;
+            nacc[r] = a.n_accept[gg];
+        }
+
+        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels:
+        // pair b of sub-step j gives z[2b], z[2b+1] (odd-k lanes recompute their neighbour's pair)
+        auto propose = [&](const double (&s)[2][KQ], int64_t n, int j, double (&p)[2][KQ], bool (&eq)[2]) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int64_t gg = live[r] ? gr[r] : 0;
+                const uint64_t gid = (uint64_t)(a.chain_offset + gg);
+                bool same = true;
+#pragma unroll
+                for (int i = 0; i < KQ; i++) {
+                    const int k = 4 * i + t;
+                    double z = 0.0;
+                    if (k < d) {
+                        const int64_t zi = ((n * J + j) * d + k) * N + gg;
+                        if (a.noise_mode == YG_NOISE_INJECT) z = a.z[zi];
+                        else {
+                            double z0, z1;
+                            philox_normal_pair(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
+                            z = (k & 1) ? z1 : z0;
+                            if (a.noise_mode == YG_NOISE_RECORD && live[r]) a.z[zi] = z;
+                        }
+                    }
+                    p[r][i] = __dadd_rn(s[r][i], __dmul_rn(propL[k], z));
+                    same = same && (p[r][i] == s[r][i]);
+                }
+                // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
+                unsigned m = __ballot_sync(0xffffffffu, same);
+                eq[r] = ((m >> (4 * g)) & 0xFu) == 0xFu;
+            }
+        };
+
+        for (int64_t n = 0; n < a.n_steps; n++) {
+            const uint64_t step = (uint64_t)(a.step0 + n);
+            // FullDiagnostics: Welford of the pre-transition state (diagnostics.py:91-94), diagonal M2.
+            // The accumulators stay in (L2-resident) global memory: the registers hold the GEMM operands.
+            {
+                const double wn = (double)(a.welford_n0 + n + 1);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    if (!live[r]) continue;
+#pragma unroll
+                    for (int i = 0; i < KQ; i++) {
+                        const int k = 4 * i + t;
+                        if (k < d) {
+                            double *pm = a.w_mean + (int64_t)k * N + gr[r];
+                            double *p2 = a.w_m2 + (int64_t)big_w2_index(k, d) * N + gr[r];
+                            const double m0 = *pm, dl = th[r][i] - m0, m1 = m0 + dl / wn;
+                            *pm = m1;
+                            *p2 += dl * (th[r][i] - m1);
+                        }
+                    }
+                }
+            }
+            bool accepted[2] = {false, false};
+            if (!TWO_LEVEL) {
+                double p[2][KQ];
+                bool eq[2];
+                propose(th, n, 0, p, eq);
+                double lpp[2];
+                logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int64_t gg = live[r] ? gr[r] : 0;
+                    if (!eq[r]) {                                           // metropolisHastings.py:60-61
+                        if (t == 0 && live[r]) cnt_ev0++;
+                        double u;
+                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
+                        else {
+                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, YG_SUB_FINE);
+                            if (a.noise_mode == YG_NOISE_RECORD && live[r] && t == 0) a.u_f[n * N + gg] = u;
+                        }
+                        if (accept_rule(lpp[r] - lp0[r], u)) {
+#pragma unroll
+                            for (int i = 0; i < KQ; i++) th[r][i] = p[r][i];
+                            lp0[r] = lpp[r];
+                            accepted[r] = true;
+                        }
+                    }
+                }
+            } else {
+                double s[2][KQ], p[2][KQ], lps[2] = {lp0[0], lp0[1]};
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int i = 0; i < KQ; i++) s[r][i] = th[r][i];
+                for (int j = 0; j < J; j++) {                               // coarse sub-chain, mlda.py:100-110
+                    bool eq[2];
+                    propose(s, n, j, p, eq);
+                    double lpp[2];
+                    logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int64_t gg = live[r] ? gr[r] : 0;
+                        if (eq[r]) continue;
+                        if (t == 0 && live[r]) cnt_ev0++;
+                        const int64_t ui = (n * J + j) * N + gg;
+                        double u;
+                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
+                        else {
+                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, (uint32_t)j);
+                            if (a.noise_mode == YG_NOISE_RECORD && live[r] && t == 0) a.u_c[ui] = u;
+                        }
+                        if (accept_rule(lpp[r] - lps[r], u)) {
+#pragma unroll
+                            for (int i = 0; i < KQ; i++) s[r][i] = p[r][i];
+                            lps[r] = lpp[r];
+                        }
+                    }
+                }
+                // the sub-chain's end point is the proposal; no fine evaluation for a chain that did
+                // not move (metropolisHastings.py:60-61).  The GEMM is warp wide: it runs when ANY of
+                // the 16 chains moved, and only the chains that moved use (and count) its result.
+                bool moved[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    bool same = true;
+#pragma unroll
+                    for (int i = 0; i < KQ; i++) same = same && (s[r][i] == th[r][i]);
+                    const unsigned m = __ballot_sync(0xffffffffu, same);
+                    moved[r] = (((m >> (4 * g)) & 0xFu) != 0xFu) && live[r];
+                }
+                if (__any_sync(0xffffffffu, moved[0] || moved[1])) {
+                    double lpf[2];
+                    logpost_tile<KQ>(Lv[1], ks, s, g, t, lpf[0], lpf[1]);
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int64_t gg = live[r] ? gr[r] : 0;
+                        if (!moved[r]) continue;
+                        if (t == 0) cnt_ev1++;
+                        double u;
+                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
+                        else {
+                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, YG_SUB_FINE);
+                            if (a.noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
+                        }
+                        const double delta = lpf[r] + lp0[r] - lps[r] - lp1[r];     // mlda.py:148-152, this order
+                        if (accept_rule(delta, u)) {
+#pragma unroll
+                            for (int i = 0; i < KQ; i++) th[r][i] = s[r][i];
+                            lp0[r] = lps[r];
+                            lp1[r] = lpf[r];
+                            accepted[r] = true;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (!live[r]) continue;
+                if (accepted[r]) { nacc[r]++; if (t == 0) cnt_acc++; }
+                if (t == 0) {
+                    cnt_tr++;
+                    if (a.accepted) a.accepted[n * N + gr[r]] = accepted[r] ? 1 : 0;
+                }
+                if ((n + 1) % a.thin == 0) {
+                    const int64_t o = (n + 1) / a.thin - 1;
+                    if (a.samples) {
+#pragma unroll
+                        for (int i = 0; i < KQ; i++)
+                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr[r]] = th[r][i];
+                    }
+                    if (a.lp_out && t == 0) {
+                        a.lp_out[(o * n_lvl) * N + gr[r]] = lp0[r];
+                        if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + gr[r]] = lp1[r];
+                    }
+                }
+            }
+        }
+        // ---- store chain state ------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (!live[r]) continue;
+#pragma unroll
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                if (k < d) a.theta[(int64_t)k * N + gr[r]] = th[r][i];
+            }
+            if (t == 0) {
+                a.logpost[gr[r]] = lp0[r];
+                if (TWO_LEVEL) a.logpost[N + gr[r]] = lp1[r];
+                a.n_accept[gr[r]] = nacc[r];
+            }
+        }
+    }
+    // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
+    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if (lane == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
+    }
+}
+
+// log-posterior of arbitrary points, one chain per thread, plain loops over global memory
+// (yg_set_state / yg_logpost: outside the step loop).
+__global__ void big_logpost_kernel(const DevBigHeader *gh, int lvl, const double *theta, int64_t n, double *out)
+{
+    const DevBigHeader &H = *gh;
+    const double *tail = reinterpret_cast<const double *>(gh + 1);
+    const BigLevel &L = H.lvl[lvl];
+    const double *G = tail + L.G_off, *bd = tail + L.bd_off, *nw = tail + L.nw_off;
+    const double *pm = tail + L.pmean_off, *pw = tail + L.pprec_off;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int col = 0; col < L.data_dim; col++) {
+            double f = 0.0;
+            for (int k = 0; k < H.dim; k++) f = fma(G[(size_t)col * H.ks + k], theta[(int64_t)k * n + c], f);
+            const double e = f + bd[col];
+            s = fma(nw[col] * e, e, s);
+        }
+        s += L.q_const;
+        double p = 0.0;
+        for (int k = 0; k < H.dim; k++) {
+            const double x = theta[(int64_t)k * n + c] - pm[k];
+            p = fma(pw[k] * x, x, p);
+        }
+        out[c] = -0.5 * s + (-0.5 * p);
+    }
+}
+
+// FP64 tensor-path micro-benchmark: independent m16n8k4 accumulator chains, 8 warps per SM.
+__global__ void __launch_bounds__(256, 1) dmma_peak_kernel(double *sink, int iters, double x)
+{
+    double c[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.0;
+    const double a0 = x + threadIdx.x * 1e-9, a1 = x - threadIdx.x * 1e-9, b0 = 1.0 + 1e-9 * threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) dmma_m16n8k4(c[k][0], c[k][1], c[k][2], c[k][3], a0, a1, b0);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1] + c[k][2] + c[k][3];
+    if (s == 123.456) sink[0] = s;
+}
+
+template <int KQ>
+int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
+{
+    const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
+    const size_t smem = sizeof(double) * (size_t)hh->tail_len;
+    auto kern = e->cfg.n_levels == 2 ? linear_dmma_mh_kernel<KQ, true> : linear_dmma_mh_kernel<KQ, false>;
+    YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = (a.n_chains + 15) / 16;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, e->sm_count));
+    kern<<<grid, 256, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem));
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->last_grid = grid;
+    e->last_block = 256;
+    e->last_smem = (int)smem;
+    e->launches += 1;
+    return YG_OK;
+}
+
+}  // namespace
+
+int yg_launch_linear_big(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
+{
+    const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
+    switch (hh->kp / 4) {
+    case 1: case 2: case 3: case 4: return launch_t<4>(e, a, st);
+    case 5: case 6: case 7: case 8: return launch_t<8>(e, a, st);
+    default: return launch_t<16>(e, a, st);
+    }
+}
+
+int yg_launch_logpost_big(yg_ensemble *e, int level, const double *theta, int64_t n, double *out, cudaStream_t st)
+{
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)e->sm_count * 16));
+    big_logpost_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const DevBigHeader *>(e->d_problem), level, theta, n, out);
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->launches += 1;
+    return YG_OK;
+}
+
+int yg_dmma_peak(int device, double ms, double *tflops_out)
+{
+    YG_CUDA_CHECK(cudaSetDevice(device));
+    int sms = 148;
+    YG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double *sink = nullptr;
+    YG_CUDA_CHECK(cudaMalloc((void **)&sink, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<sms, 256>>>(sink, iters, 1.0);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        const double flop = 2.0 * 16 * 8 * 4 * 8.0 * iters * 8.0 * sms;       // per mma x 8 chains x 8 warps x SMs
+        if (rep > 0) best = std::max(best, flop / (t * 1e-3) / 1e12);
+        if (t < ms / 6.0) iters *= 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    YG_CUDA_CHECK(cudaGetLastError());
+    *tflops_out = best;
+    return YG_OK;
+}

@@ -202,8 +202,10 @@ class ChainEnsemble:
     def state(self):
         n, d = self.n_chains, self.dim
         st = YgState()
+        # large linear model (d > YG_MAX_DIM): Welford M2 is diagonal only, [d, n]
+        w_m2 = self._empty(d, d, n) if d <= _lib.YG_MAX_DIM else self._empty(d, n)
         r = dict(theta=self._empty(d, n), logpost=self._empty(self.levels, n),
-                 n_accept=self._empty(n, dtype=torch.int64), w_mean=self._empty(d, n), w_m2=self._empty(d, d, n))
+                 n_accept=self._empty(n, dtype=torch.int64), w_mean=self._empty(d, n), w_m2=w_m2)
         st.theta_dev, st.logpost_dev, st.n_accept_dev = r['theta'].data_ptr(), r['logpost'].data_ptr(), r['n_accept'].data_ptr()
         st.w_mean_dev, st.w_m2_dev = r['w_mean'].data_ptr(), r['w_m2'].data_ptr()
         if self.cfg.adaptive:
@@ -303,4 +305,12 @@ def fp64_peak_tflops(device=0, ms=20.0):
     lib = _lib.load()
     out = C.c_double()
     check(lib.yg_fp64_peak(int(device), float(ms), C.byref(out)))
+    return out.value
+
+
+def fp64_tensor_peak_tflops(device=0, ms=20.0):
+    """FP64 tensor-path (DMMA) micro-benchmark: the roofline denominator of the large linear model."""
+    lib = _lib.load()
+    out = C.c_double()
+    check(lib.yg_fp64_tensor_peak(int(device), float(ms), C.byref(out)))
     return out.value
