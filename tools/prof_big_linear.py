@@ -1,0 +1,15 @@
+"""Dev tool: one short run of the DMMA linear kernel (for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench_problems as bp
+from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem
+nc = 65536
+meta, arrays = bp.big_linear_problem(64, 256, 1)
+ens = ChainEnsemble(LoweredProblem(meta, arrays), nc, seed=1)
+mean, _ = bp.linear_gaussian_posterior(arrays, 0)
+ens.set_state(np.tile(mean, (nc, 1)))
+for _ in range(3):
+    ens.run(10, samples=False)
+torch.cuda.synchronize()
+print("ok", ens.counters())

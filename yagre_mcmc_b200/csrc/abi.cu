@@ -134,7 +134,7 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     }
     tail_len += kp;
     tail_len = (tail_len + 1) & ~size_t(1);
-    if (sizeof(double) * tail_len > 216 * 1024) {
+    if (sizeof(double) * (tail_len + (size_t)8 * 16 * ks) > 226 * 1024) {      // blob + per-warp state tiles
         yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
         return YG_ERR_UNSUPPORTED;
     }

@@ -15,9 +15,10 @@
 //
 // B200 mapping
 //   * persistent CTAs (one per SM), 8 warps; a warp owns a tile of 16 chains (the M extent of
-//     m16n8k4) for ALL n_steps.  The chain state lives in registers in A-fragment layout: lane
-//     (g = lane / 4, t = lane % 4) holds theta[row g and g+8][k = 4 i + t], so a proposal is
-//     already the A operand of the GEMM -- no shared-memory round trip for the chain state;
+//     m16n8k4) for ALL n_steps.  Proposals live in registers in A-fragment layout: lane
+//     (g = lane / 4, t = lane % 4) holds p[row g and g+8][k = 4 i + t], so a proposal is already
+//     the A operand of the GEMM; the current state of the tile sits in a per-warp shared-memory
+//     tile in the same lane-private pattern (d = 64 needs 64 registers per operand copy);
 //   * G of every level is staged once per CTA into shared memory (row stride = 4 mod 16 doubles:
 //     the B-fragment loads of a warp are bank-conflict free) and shared by the 8 warps; with 16
 //     chains per B fragment the shared-memory traffic is 1/2 of the DMMA issue time;
@@ -66,16 +67,32 @@ YG_DEVFN void logpost_tile(const SmemLevel &L, const int ks, const double (&a)[2
     // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + q_const  (exact identity;
     // no cancellation: the row scatter is a precomputed constant)
     double q0 = 0.0, q1 = 0.0;
-    for (int nb = 0; nb < L.np; nb += 8) {
-        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
-#pragma unroll
-        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, a[0][i], a[1][i], Gb[4 * i]);
+    auto epilogue = [&](const int nb, const double c0, const double c1, const double c2, const double c3) {
         const int col = nb + 2 * t;
         const double b0 = L.bd[col], b1 = L.bd[col + 1], w0 = L.nw[col], w1 = L.nw[col + 1];
         const double e00 = c0 + b0, e01 = c1 + b1, e10 = c2 + b0, e11 = c3 + b1;     // A @ theta + b - mean(data)
         q0 = fma(w1 * e01, e01, fma(w0 * e00, e00, q0));
         q1 = fma(w1 * e11, e11, fma(w0 * e10, e10, q1));
+    };
+    // two independent accumulator tiles per pass: a chain of dependent DMMAs alone cannot fill the pipe
+    int nb = 0;
+    for (; nb + 16 <= L.np; nb += 16) {
+        double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+        const double *Gb0 = L.G + (size_t)(nb + g) * ks + t, *Gb1 = Gb0 + (size_t)8 * ks;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) {
+            dmma_m16n8k4(c[0][0], c[0][1], c[0][2], c[0][3], a[0][i], a[1][i], Gb0[4 * i]);
+            dmma_m16n8k4(c[1][0], c[1][1], c[1][2], c[1][3], a[0][i], a[1][i], Gb1[4 * i]);
+        }
+        epilogue(nb, c[0][0], c[0][1], c[0][2], c[0][3]);
+        epilogue(nb + 8, c[1][0], c[1][1], c[1][2], c[1][3]);
+    }
+    for (; nb < L.np; nb += 8) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, a[0][i], a[1][i], Gb[4 * i]);
+        epilogue(nb, c0, c1, c2, c3);
     }
     const double s0 = quad_sum(q0) + L.q_const, s1 = quad_sum(q1) + L.q_const;
     double p0 = 0.0, p1 = 0.0;
@@ -112,6 +129,11 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
         Lv[l].np = H.lvl[l].np;
     }
     const double *propL = smem + H.propL_off;      // [kp] diagonal proposal factor (zero beyond dim)
+    // current state of the warp's 16 chains: [16][ks] doubles after the problem blob; lane (g, t) only
+    // ever touches its own slots (rows g, g+8, columns 4 i + t), so no synchronisation is needed, and
+    // the row stride (4 mod 16 doubles) makes the accesses bank-conflict free
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * 16 * H.ks;
+#define TH(r, i) ths[((r) * 8 + g) * ks + 4 * (i) + t]
     const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
@@ -121,7 +143,6 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
         // rows of this lane: chains gr[0], gr[1] (a row beyond n_chains is computed but never stored)
         int64_t gr[2] = {tile * 16 + g, tile * 16 + g + 8};
         bool live[2] = {gr[0] < N, gr[1] < N};
-        double th[2][KQ];
         double lp0[2], lp1[2];
         unsigned long long nacc[2];
 #pragma unroll
@@ -131,71 +152,119 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
                 const bool in = k < d;
-                th[r][i] = in ? a.theta[(int64_t)k * N + gg] : 0.0;
+                TH(r, i) = in ? a.theta[(int64_t)k * N + gg] : 0.0;
             }
             lp0[r] = a.logpost[gg];
             lp1[r] = TWO_LEVEL ? a.logpost[N + gg] : 0.0;
             nacc[r] = a.n_accept[gg];
         }
 
-        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels:
-        // pair b of sub-step j gives z[2b], z[2b+1] (odd-k lanes recompute their neighbour's pair)
-        auto propose = [&](const double (&s)[2][KQ], int64_t n, int j, double (&p)[2][KQ], bool (&eq)[2]) {
+        // Welford (estimation.py:36-53, diagonal M2) in run-length form: a chain that stays at x for m
+        // consecutive steps contributes  n' = n + m, mean' = mean + (x - mean) m / n',
+        // M2' = M2 + (x - mean)^2 n m / n'  -- algebraically the m sequential updates.  With the
+        // accumulators in (L2-resident) global memory this touches them once per accepted move
+        // instead of once per step; the registers stay with the GEMM operands.
+        double run[2] = {0.0, 0.0}, wn[2] = {(double)a.welford_n0, (double)a.welford_n0};
+        // flush[r]: row r leaves its state now.  Both rows go through ONE pass with the loads of a
+        // batch of columns issued before any store (a store may alias the next load for the compiler).
+        auto welford_flush = [&](const bool f0, const bool f1) {
+            const bool fl[2] = {f0 && live[0] && run[0] != 0.0, f1 && live[1] && run[1] != 0.0};
+            if (!__any_sync(0xffffffffu, fl[0] || fl[1])) return;
+            double c1[2], c2[2];
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                const int64_t gg = live[r] ? gr[r] : 0;
-                const uint64_t gid = (uint64_t)(a.chain_offset + gg);
-                bool same = true;
+                const double n1 = wn[r] + run[r];
+                c1[r] = run[r] / n1;
+                c2[r] = wn[r] * c1[r];
+            }
+            constexpr int B = KQ < 4 ? KQ : 4;
 #pragma unroll
-                for (int i = 0; i < KQ; i++) {
-                    const int k = 4 * i + t;
-                    double z = 0.0;
-                    if (k < d) {
-                        const int64_t zi = ((n * J + j) * d + k) * N + gg;
-                        if (a.noise_mode == YG_NOISE_INJECT) z = a.z[zi];
-                        else {
-                            double z0, z1;
-                            philox_normal_pair(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
-                            z = (k & 1) ? z1 : z0;
-                            if (a.noise_mode == YG_NOISE_RECORD && live[r]) a.z[zi] = z;
+            for (int i0 = 0; i0 < KQ; i0 += B) {
+                double m0[2][B], v0[2][B];
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int i = 0; i < B; i++) {
+                        const int k = 4 * (i0 + i) + t;
+                        const bool on = fl[r] && k < d;
+                        m0[r][i] = on ? a.w_mean[(int64_t)k * N + gr[r]] : 0.0;
+                        v0[r][i] = on ? a.w_m2[(int64_t)big_w2_index(k, d) * N + gr[r]] : 0.0;
+                    }
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int i = 0; i < B; i++) {
+                        const int k = 4 * (i0 + i) + t;
+                        if (fl[r] && k < d) {
+                            const double dl = TH(r, i0 + i) - m0[r][i];
+                            a.w_mean[(int64_t)k * N + gr[r]] = fma(dl, c1[r], m0[r][i]);
+                            a.w_m2[(int64_t)big_w2_index(k, d) * N + gr[r]] = fma(dl * dl, c2[r], v0[r][i]);
                         }
                     }
-                    p[r][i] = __dadd_rn(s[r][i], __dmul_rn(propL[k], z));
-                    same = same && (p[r][i] == s[r][i]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+                if (fl[r]) { wn[r] += run[r]; run[r] = 0.0; }
+        };
+
+        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels:
+        // pair b of sub-step j gives z[2b], z[2b+1].  The even lane of a lane pair draws the pair for
+        // row g, the odd lane for row g+8, and they swap the halves they do not own: one Philox block
+        // and one Box-Muller per lane and 4 parameters.
+        auto propose = [&](auto &&src, int64_t n, int j, double (&p)[2][KQ], bool (&eq)[2]) {
+            const int odd = t & 1;
+            const int64_t g_mine = odd ? (live[1] ? gr[1] : 0) : (live[0] ? gr[0] : 0);
+            const uint64_t gid = (uint64_t)(a.chain_offset + g_mine);
+            bool same[2] = {true, true};
+#pragma unroll
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                double zr[2] = {0.0, 0.0};
+                if (a.noise_mode == YG_NOISE_INJECT) {
+                    if (k < d) {
+#pragma unroll
+                        for (int r = 0; r < 2; r++) zr[r] = a.z[((n * J + j) * d + k) * N + (live[r] ? gr[r] : 0)];
+                    }
+                } else {
+                    // no branch on k < d: straight-line code lets the scheduler interleave the KQ
+                    // independent Philox / Box-Muller chains (padding columns are zeroed below)
+                    double z0, z1;
+                    philox_normal_pair(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
+                    const double recv = __shfl_xor_sync(0xffffffffu, odd ? z0 : z1, 1);
+                    zr[0] = odd ? recv : z0;
+                    zr[1] = odd ? z1 : recv;
+                    if (k >= d) zr[0] = zr[1] = 0.0;
+                    if (a.noise_mode == YG_NOISE_RECORD && k < d) {
+#pragma unroll
+                        for (int r = 0; r < 2; r++)
+                            if (live[r]) a.z[((n * J + j) * d + k) * N + gr[r]] = zr[r];
+                    }
                 }
-                // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
-                unsigned m = __ballot_sync(0xffffffffu, same);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const double sv = src(r, i);
+                    p[r][i] = __dadd_rn(sv, __dmul_rn(propL[k], zr[r]));
+                    same[r] = same[r] && (p[r][i] == sv);
+                }
+            }
+            // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const unsigned m = __ballot_sync(0xffffffffu, same[r]);
                 eq[r] = ((m >> (4 * g)) & 0xFu) == 0xFu;
             }
         };
 
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
-            // FullDiagnostics: Welford of the pre-transition state (diagnostics.py:91-94), diagonal M2.
-            // The accumulators stay in (L2-resident) global memory: the registers hold the GEMM operands.
-            {
-                const double wn = (double)(a.welford_n0 + n + 1);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    if (!live[r]) continue;
-#pragma unroll
-                    for (int i = 0; i < KQ; i++) {
-                        const int k = 4 * i + t;
-                        if (k < d) {
-                            double *pm = a.w_mean + (int64_t)k * N + gr[r];
-                            double *p2 = a.w_m2 + (int64_t)big_w2_index(k, d) * N + gr[r];
-                            const double m0 = *pm, dl = th[r][i] - m0, m1 = m0 + dl / wn;
-                            *pm = m1;
-                            *p2 += dl * (th[r][i] - m1);
-                        }
-                    }
-                }
-            }
+            // FullDiagnostics: Welford of the pre-transition state (diagnostics.py:91-94): the state of
+            // this step is seen once more; the accumulators are touched when the state changes.
+            run[0] += 1.0; run[1] += 1.0;
             bool accepted[2] = {false, false};
             if (!TWO_LEVEL) {
                 double p[2][KQ];
                 bool eq[2];
-                propose(th, n, 0, p, eq);
+                propose([&](int r, int i) { return TH(r, i); }, n, 0, p, eq);
                 double lpp[2];
                 logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
 #pragma unroll
@@ -209,12 +278,16 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
                             u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, YG_SUB_FINE);
                             if (a.noise_mode == YG_NOISE_RECORD && live[r] && t == 0) a.u_f[n * N + gg] = u;
                         }
-                        if (accept_rule(lpp[r] - lp0[r], u)) {
+                        accepted[r] = accept_rule(lpp[r] - lp0[r], u);
+                    }
+                }
+                welford_flush(accepted[0], accepted[1]);
 #pragma unroll
-                            for (int i = 0; i < KQ; i++) th[r][i] = p[r][i];
-                            lp0[r] = lpp[r];
-                            accepted[r] = true;
-                        }
+                for (int r = 0; r < 2; r++) {
+                    if (accepted[r]) {
+#pragma unroll
+                        for (int i = 0; i < KQ; i++) TH(r, i) = p[r][i];
+                        lp0[r] = lpp[r];
                     }
                 }
             } else {
@@ -222,10 +295,10 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
 #pragma unroll
                 for (int r = 0; r < 2; r++)
 #pragma unroll
-                    for (int i = 0; i < KQ; i++) s[r][i] = th[r][i];
+                    for (int i = 0; i < KQ; i++) s[r][i] = TH(r, i);
                 for (int j = 0; j < J; j++) {                               // coarse sub-chain, mlda.py:100-110
                     bool eq[2];
-                    propose(s, n, j, p, eq);
+                    propose([&](int r, int i) { return s[r][i]; }, n, j, p, eq);
                     double lpp[2];
                     logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
 #pragma unroll
@@ -255,7 +328,7 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
                 for (int r = 0; r < 2; r++) {
                     bool same = true;
 #pragma unroll
-                    for (int i = 0; i < KQ; i++) same = same && (s[r][i] == th[r][i]);
+                    for (int i = 0; i < KQ; i++) same = same && (s[r][i] == TH(r, i));
                     const unsigned m = __ballot_sync(0xffffffffu, same);
                     moved[r] = (((m >> (4 * g)) & 0xFu) != 0xFu) && live[r];
                 }
@@ -274,12 +347,16 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
                             if (a.noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
                         }
                         const double delta = lpf[r] + lp0[r] - lps[r] - lp1[r];     // mlda.py:148-152, this order
-                        if (accept_rule(delta, u)) {
+                        accepted[r] = accept_rule(delta, u);
+                    }
+                    welford_flush(accepted[0], accepted[1]);
 #pragma unroll
-                            for (int i = 0; i < KQ; i++) th[r][i] = s[r][i];
+                    for (int r = 0; r < 2; r++) {
+                        if (accepted[r]) {
+#pragma unroll
+                            for (int i = 0; i < KQ; i++) TH(r, i) = s[r][i];
                             lp0[r] = lps[r];
                             lp1[r] = lpf[r];
-                            accepted[r] = true;
                         }
                     }
                 }
@@ -297,7 +374,7 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
                     if (a.samples) {
 #pragma unroll
                         for (int i = 0; i < KQ; i++)
-                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr[r]] = th[r][i];
+                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr[r]] = TH(r, i);
                     }
                     if (a.lp_out && t == 0) {
                         a.lp_out[(o * n_lvl) * N + gr[r]] = lp0[r];
@@ -307,13 +384,14 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
             }
         }
         // ---- store chain state ------------------------------------------------------------------
+        welford_flush(true, true);
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             if (!live[r]) continue;
 #pragma unroll
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
-                if (k < d) a.theta[(int64_t)k * N + gr[r]] = th[r][i];
+                if (k < d) a.theta[(int64_t)k * N + gr[r]] = TH(r, i);
             }
             if (t == 0) {
                 a.logpost[gr[r]] = lp0[r];
@@ -322,6 +400,7 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
             }
         }
     }
+#undef TH
     // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
     unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
 #pragma unroll
@@ -381,7 +460,7 @@ template <int KQ>
 int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
-    const size_t smem = sizeof(double) * (size_t)hh->tail_len;
+    const size_t smem = sizeof(double) * ((((size_t)hh->tail_len + 1) & ~size_t(1)) + (size_t)8 * 16 * hh->ks);
     auto kern = e->cfg.n_levels == 2 ? linear_dmma_mh_kernel<KQ, true> : linear_dmma_mh_kernel<KQ, false>;
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n_chains + 15) / 16;
