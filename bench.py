@@ -291,6 +291,11 @@ def run_gpu_arm(args):
                              "summed over chains / sampling wall time (burn-in included)"}
         del out
 
+    # ---- the other BASELINE.json configs, briefly (rank 0, N = 1): parity-tested elsewhere, timed here ----
+    others = None
+    if n_gpus == 1 and not args.no_configs:
+        others = measure_other_configs(local, peak)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,6 +329,7 @@ def run_gpu_arm(args):
         "cpu_baseline": cpu,
         "e2e": e2e,
         "ess": ess,
+        "other_configs": others,
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "launch": ens.last_launch(),
@@ -331,6 +337,70 @@ def run_gpu_arm(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_other_configs(device, fp64_peak):
+    """Device-timed chain-steps/s of C2, C3, C4 and the GEMM-sized linear model (state resident in HBM, 3 timed
+    launches after a warm-up launch each).  Secondary numbers: the headline stays the C5 line."""
+    import torch
+    from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem, fp64_tensor_peak_tflops
+
+    def timed(ens, steps, reps=3):
+        ens.run(steps, samples=False)
+        torch.cuda.synchronize()
+        c0 = ens.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ens.run(steps, samples=False)
+        e1.record()
+        torch.cuda.synchronize()
+        c1 = ens.counters()
+        ms = e0.elapsed_time(e1)
+        return ms, {k: c1[k] - c0[k] for k in ("transitions", "accepted", "coarse_evals", "fine_evals")}
+
+    out = {}
+    # C4: LV single level, 65,536 chains
+    meta, arrays = bp.lv_problem(False)
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5)
+    ens.set_state(bp.lv_initial_states(65536))
+    ms, c = timed(ens, 20)
+    fl = bp.lv_flops_per_eval(meta["n_data"], meta["Nf"]) * c["fine_evals"]
+    out["C4_lv_single_level_65536"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                                       "fp64_tflops": fl / ms * 1e-9, "frac_of_fp64_peak": fl / ms * 1e-9 / fp64_peak,
+                                       "kernel": "lv_mh_kernel<false>"}
+    ens.close()
+    # C3: linear two level (J = 5), 16,384 chains -- a few hundred FP64 instructions per step, launch / issue bound
+    meta, arrays = bp.linear_problem(True)
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 16384, device=device, seed=5)
+    ens.set_state(np.zeros((16384, 2)))
+    ms, c = timed(ens, 5000)
+    out["C3_linear_two_level_16384"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                                        "kernel": "generic_mh_kernel<2,2,true>"}
+    ens.close()
+    # C2: 2-D Gaussian target, per-chain adaptive Metropolis, 4,096 chains
+    meta, arrays = bp.gauss2d_problem()
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 4096, device=device, seed=5,
+                        adaptive=dict(idle=5000, collection=5000, eps=1e-4))
+    ens.set_state(np.tile([-8.0, -7.0], (4096, 1)))
+    ens.run(12000, samples=False)
+    ms, c = timed(ens, 5000)
+    out["C2_gauss2d_adaptive_4096"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                                       "kernel": "generic_mh_kernel<2,2,false> (adaptive)"}
+    ens.close()
+    # GEMM-sized linear model (SURVEY 8d variant): d = 64, dataDim = 256, 65,536 chains, FP64 tensor path
+    meta, arrays = bp.big_linear_problem(64, 256, 1)
+    mean, _ = bp.linear_gaussian_posterior(arrays, 0)
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5)
+    ens.set_state(np.tile(mean, (65536, 1)))
+    ms, c = timed(ens, 50)
+    fl = bp.big_linear_flops_per_eval(64, 256) * (c["coarse_evals"] + c["fine_evals"])
+    tpeak = fp64_tensor_peak_tflops(device, 20.0)
+    out["linear_d64_x256_65536"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                                    "fp64_tflops": fl / ms * 1e-9, "dmma_peak_tflops": tpeak, "frac_of_dmma_peak": fl / ms * 1e-9 / tpeak,
+                                    "kernel": "linear_dmma_mh_kernel<16,false>"}
+    ens.close()
+    return out
 
 
 def main():
@@ -349,6 +419,7 @@ def main():
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the brief timing of the other BASELINE.json configs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else args.warmup
