@@ -24,7 +24,8 @@
  *                            MRWProposal mrw.py:27-38, PCNProposal pcn.py:23-35, _accept_reject :55-73,
  *                            MLDAProposal.generate_proposal mlda.py:100-110 and
  *                            MLDA._acceptance_probability mlda.py:146-154,
- *                            AdaptiveMRWProposal.set_state chain/adaptive.py:55-60
+ *                            AdaptiveMRWProposal.set_state chain/adaptive.py:55-60,
+ *                            AdaptiveErrorModel._process_transition chain/method/aem.py:25-58
  *   yg_get_state/yg_load_state   .chain.trajectory[-1] restart idiom
  *                            (example_inference_linearModel_twoLevel.py:228,236) + diagnostics
  *                            (AcceptanceRateDiagnostics / FullDiagnostics chain/diagnostics.py:19-107,
@@ -60,7 +61,7 @@
 extern "C" {
 #endif
 
-#define YG_ABI_VERSION 2u
+#define YG_ABI_VERSION 3u
 #define YG_MAX_DIM 8           /* parameter dimension of the one-chain-per-thread kernels */
 #define YG_MAX_DATA_DIM 8
 /* YG_MODEL_LINEAR beyond those sizes runs on the FP64 tensor path (DMMA GEMM, linear_dmma_kernel.cu):
@@ -141,7 +142,15 @@ typedef struct yg_config {
     int32_t blocks_per_sm;      /* 0 = default; tuning knob of the LV kernel */
     int32_t threads_per_block;  /* 0 = default */
     int32_t rk4_segment;        /* 0 = default (128): RK4 steps per work unit of the LV kernel */
-    int32_t reserved[5];
+    /* adaptive error model (chain/method/aem.py, statistics/likelihood.py:90-155, statistics/noise.py:25-61):
+     * n_levels == 2, YG_MODEL_LINEAR (dim, data_dim <= 8), diagonal measurement noise.  Per chain: Welford of
+     * F_fine - F_coarse on accepted fine steps; the coarse residual is shifted by its mean once aem_min_data
+     * errors were seen, the noise variance is inflated by (scaling x) its variance from aem_min_data + 1 on; the
+     * coarse likelihood's LRU(3) cache is reproduced, including that cached values survive model updates. */
+    int32_t aem;                /* 0 / 1 */
+    int32_t aem_min_data;       /* minDataSize >= 2 */
+    int32_t aem_heuristic;      /* useNoiseHeuristic: scaling = min(2 max(var) / max(min(var), 1e-6), 100) */
+    int32_t reserved[2];
 } yg_config;
 
 typedef struct yg_noise {
@@ -168,6 +177,11 @@ typedef struct yg_state {
     double *prop_L_dev;         /* [d, d, n_chains] current proposal factor (adaptive only) */
     double *am_mean_dev;        /* [d, n_chains]    adaptive Metropolis running mean (adaptive only) */
     double *am_m2_dev;          /* [d, d, n_chains] adaptive Metropolis second central moment (adaptive only) */
+    /* adaptive error model only */
+    int64_t *aem_n_dev;         /* [n_chains] error realisations seen (WelfordAccumulator.nData) */
+    double *aem_mean_dev;       /* [data_dim, n_chains] mean of F_fine - F_coarse */
+    double *aem_m2_dev;         /* [data_dim, n_chains] second central moment (variance = m2 / (n - 1)) */
+    double *aem_cache_dev;      /* [3 (d + 1) + 1, n_chains] coarse LRU(3): keys, values, entry count (oldest first) */
 } yg_state;
 
 const char *yg_last_error(void);

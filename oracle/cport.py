@@ -31,7 +31,8 @@ class YoProblem(C.Structure):
                 ("adaptive", C.c_int32), ("am_refresh", C.c_int32), ("am_idle", C.c_int64),
                 ("am_collect", C.c_int64), ("am_eps", C.c_double), ("am_scale", C.c_double),
                 ("pcn", C.c_int32), ("_pad2", C.c_int32), ("pcn_a", C.c_double), ("pcn_b", C.c_double),
-                ("pcn_mean", _dp)]
+                ("pcn_mean", _dp),
+                ("aem", C.c_int32), ("aem_min_data", C.c_int32), ("aem_heuristic", C.c_int32), ("_pad3", C.c_int32)]
 
 
 def build(force=False):
@@ -93,6 +94,9 @@ class Problem:
             self.keep['pcn_mean'] = _arr(arrays.get('pcn_mean', np.zeros(int(meta['dim']))))
             pb.pcn_mean = _ptr(self.keep['pcn_mean'])
 
+        if meta.get('aem'):
+            pb.aem, pb.aem_min_data, pb.aem_heuristic = 1, int(meta['aem']['min_data']), int(bool(meta['aem']['heuristic']))
+
         def put(obj, field, key):
             if key in arrays:
                 a = _arr(arrays[key])
@@ -128,13 +132,19 @@ def run_injected(problem, theta0, z, u_c, u_f, n_threads=0):
     wm = np.empty((nc, d))
     wv = np.empty((nc, d))
     ev = np.zeros(2, dtype=np.int64)
+    dd = int(problem.pb.level[0].data_dim)
+    aem = np.zeros((nc, 2 + 2 * max(dd, 1)))
     rc = lib().yo_run_injected(C.byref(problem.pb), C.c_int64(nc), C.c_int64(ns),
                                _ptr(theta0), _ptr(z), _ptr(u_c), _ptr(u_f), _ptr(traj),
                                acc.ctypes.data_as(C.c_void_p), _ptr(lp0), _ptr(lp1), _ptr(wm), _ptr(wv),
-                               ev.ctypes.data_as(C.c_void_p), C.c_int(n_threads))
+                               ev.ctypes.data_as(C.c_void_p), C.c_int(n_threads), _ptr(aem))
     assert rc == 0
-    return dict(traj=traj, accepted=acc, logpost_L0=lp0, logpost_L1=lp1,
-                welford_mean=wm, welford_var=wv, n_evals=ev)
+    out = dict(traj=traj, accepted=acc, logpost_L0=lp0, logpost_L1=lp1,
+               welford_mean=wm, welford_var=wv, n_evals=ev)
+    if problem.pb.aem:
+        out.update(aem_n=aem[:, 0].astype(np.int64), aem_model_evals=aem[:, 1].astype(np.int64),
+                   aem_mean=aem[:, 2:2 + dd], aem_var=aem[:, 2 + dd:2 + 2 * dd])
+    return out
 
 
 def run_philox(problem, theta, seed, n_steps, chain_offset=0, step0=0, thin=1, store=True, n_threads=0):

@@ -483,6 +483,53 @@ def cases_pcn():
 
 
 # --------------------------------------------------------------------------
+# adaptive error model (chain/method/aem.py, statistics/likelihood.py:90-155, statistics/noise.py:25-61;
+# example_inference_linearModel_twoLevel.py:95-102,183-191)
+# --------------------------------------------------------------------------
+
+def case_aem(name, minDataSize, useHeuristic, nSteps, seed):
+    p = linear_problem()
+    nChains, J = 3, 5
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 4, None), (1, 8, 1)])
+    traj, acc, en, em, ev, nev = [], [], [], [], [], []
+    for c in range(nChains):
+        data = rh.Data(p['data'])
+        noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(2, p['noiseVar']))
+        prior = rh.Gaussian(rh.ParameterVector(p['priorMean']), rh.IIDCovarianceMatrix(2, p['priorVar']))
+        likC = rh.AEMLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_c'], p['b_c'])), noise, minDataSize, useHeuristic)
+        likF = rh.AEMLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_f'], p['b_f'])), noise, minDataSize, useHeuristic)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        b = rh.AEMBuilder()
+        b.bayesModel = rh.BayesianRegressionModelHierarchy(rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+        b.subChainLengths = [J]
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.zeros(2)), nSteps, inj, True)
+        traj.append(t); acc.append(a)
+        accum = likC.accumulator
+        en.append(accum.nData)
+        em.append(accum.mean() if accum.nData > 0 else np.zeros(2))
+        ev.append(accum.marginal_variance() if accum.nData > 1 else np.zeros(2))
+        nev.append([likC.number_of_model_evaluations(), likF.number_of_model_evaluations()])
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}, error samples {accum.nData}, "
+              f"model evaluations {nev[-1]}")
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], 2), theta0=np.zeros((nChains, 2)),
+                  z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc,
+                  aem_n=np.array(en), aem_mean=np.array(em), aem_var=np.array(ev), n_model_evals=np.array(nev))
+    arrays.update(linear_level_arrays(p, 'c', 'L0_'))
+    arrays.update(linear_level_arrays(p, 'f', 'L1_'))
+    meta = dict(model='linear', dim=2, levels=2, J=J, eq='exact', aem=dict(min_data=minDataSize, heuristic=bool(useHeuristic)),
+                note='AEM on C3: example_inference_linearModel_twoLevel.py:95-102,183-191')
+    save(name, meta, arrays)
+
+
+def cases_aem():
+    case_aem("aem_linear", 5, True, 400, 1500)
+    case_aem("aem_linear_noheuristic", 12, False, 400, 1501)
+
+
+# --------------------------------------------------------------------------
 # post-processing pins: IAT, Welford, dense covariance
 # --------------------------------------------------------------------------
 
@@ -549,3 +596,5 @@ if __name__ == "__main__":
         cases_lv()
     if want('pcn'):
         cases_pcn()
+    if want('aem'):
+        cases_aem()

@@ -61,6 +61,8 @@ from yagremcmc.utility.hierarchy import SharedComponent, Hierarchy           # n
 from yagremcmc.chain.method.mrw import MRWBuilder, MetropolisedRandomWalk   # noqa: E402
 from yagremcmc.chain.method.mlda import MLDABuilder              # noqa: E402
 from yagremcmc.chain.method.pcn import PCNBuilder                # noqa: E402
+from yagremcmc.chain.method.aem import AEMBuilder                # noqa: E402
+from yagremcmc.statistics.likelihood import AEMLikelihood        # noqa: E402
 from yagremcmc.chain.diagnostics import FullDiagnostics          # noqa: E402
 from yagremcmc.test.testSetup import (                           # noqa: E402
     LotkaVolterraParameter, GaussianTargetDensity1d, GaussianTargetDensity2d)

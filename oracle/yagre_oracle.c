@@ -66,6 +66,9 @@ typedef struct yo_problem {
     int32_t pcn, _pad2;
     double pcn_a, pcn_b;       /* sqrt(1 - 2h), sqrt(2h) */
     const double *pcn_mean;    /* [d] prior mean (zeros: pcn.py:44-46) */
+    /* adaptive error model (chain/method/aem.py, statistics/likelihood.py:90-155, noise.py:25-61):
+     * two levels, linear forward model, diagonal measurement noise */
+    int32_t aem, aem_min_data, aem_heuristic, _pad3;
 } yo_problem;
 
 /* ---------------------------------------------------------------------- */
@@ -336,6 +339,14 @@ typedef struct {
     double w_mean[YO_MAX_DIM], w_m2[YO_MAX_DIM];
     /* adaptive Metropolis: full-matrix Welford of the states from step am_idle on + current factor */
     double am_mean[YO_MAX_DIM], am_m2[YO_MAX_DIM * YO_MAX_DIM], L[YO_MAX_DIM * YO_MAX_DIM];
+    /* adaptive error model: Welford of F_f - F_c on accepted fine steps (estimation.py:36-53), the
+     * inflated noise precision, and the coarse likelihood's LRU(3) cache of (parameter -> logL)
+     * (utility/memoisation.py:76-149), entries ordered oldest .. newest */
+    int64_t aem_n;
+    double aem_mean[YO_MAX_DATA], aem_m2[YO_MAX_DATA], aem_prec[YO_MAX_DATA];
+    int aem_have_noise, lru_n;
+    double lru_key[3][YO_MAX_DIM], lru_ll[3];
+    int64_t aem_model_evals;
 } chain_state;
 
 int yo_cholesky(const double *C, int d, double *L);
@@ -377,6 +388,166 @@ static void welford_update(chain_state *cs, int d)
     }
 }
 
+
+/* ---------------------------------------------------------------------- */
+/* adaptive error model                                                   */
+/* ---------------------------------------------------------------------- */
+static int lru_find(const yo_problem *pb, const chain_state *cs, const double *x)
+{
+    for (int i = 0; i < cs->lru_n; i++) {
+        int eq = 1;
+        for (int k = 0; k < pb->dim; k++) eq = eq && (cs->lru_key[i][k] == x[k]);   /* vector.py:37-45 */
+        if (eq) return i;
+    }
+    return -1;
+}
+/* AEMCache._move_to_back (memoisation.py:95-100) */
+static void lru_touch(const yo_problem *pb, chain_state *cs, int idx)
+{
+    double key[YO_MAX_DIM], ll = cs->lru_ll[idx];
+    memcpy(key, cs->lru_key[idx], sizeof(double) * pb->dim);
+    for (int i = idx; i + 1 < cs->lru_n; i++) {
+        memcpy(cs->lru_key[i], cs->lru_key[i + 1], sizeof(double) * pb->dim);
+        cs->lru_ll[i] = cs->lru_ll[i + 1];
+    }
+    memcpy(cs->lru_key[cs->lru_n - 1], key, sizeof(double) * pb->dim);
+    cs->lru_ll[cs->lru_n - 1] = ll;
+}
+/* AEMCache.add (memoisation.py:102-116): evict the oldest of three */
+static void lru_add(const yo_problem *pb, chain_state *cs, const double *x, double ll)
+{
+    if (cs->lru_n >= 3) {
+        for (int i = 0; i + 1 < 3; i++) {
+            memcpy(cs->lru_key[i], cs->lru_key[i + 1], sizeof(double) * pb->dim);
+            cs->lru_ll[i] = cs->lru_ll[i + 1];
+        }
+        cs->lru_n = 2;
+    }
+    memcpy(cs->lru_key[cs->lru_n], x, sizeof(double) * pb->dim);
+    cs->lru_ll[cs->lru_n] = ll;
+    cs->lru_n++;
+}
+static void linear_forward(const yo_level *L, int d, const double *theta, double *F)
+{
+    for (int k = 0; k < L->data_dim; k++) {          /* A @ theta + b  (exampleSetup.py:46) */
+        double acc = 0.0;
+        for (int j = 0; j < d; j++) {
+            double t = L->G[k * d + j] * theta[j];
+            acc = (j == 0) ? t : acc + t;
+        }
+        F[k] = acc + L->b[k];
+    }
+}
+/* AEMLikelihood.compute_log_likelihood (likelihood.py:74-84,140-145) + prior (target.py:19-22) */
+static double aem_coarse_logpost(const yo_problem *pb, chain_state *cs, const double *x)
+{
+    const yo_level *L = &pb->level[0];
+    const int d = pb->dim, dd = L->data_dim;
+    double F[YO_MAX_DATA], q[64];
+    linear_forward(L, d, x, F);
+    cs->aem_model_evals++;
+    for (int n = 0; n < L->n_data; n++) {
+        double acc = 0.0;
+        for (int k = 0; k < dd; k++) {
+            double r = F[k] - L->data[n * dd + k];
+            if (cs->aem_n >= pb->aem_min_data) r = r + cs->aem_mean[k];              /* likelihood.py:140-145 */
+            const double prec = cs->aem_have_noise ? cs->aem_prec[k] : L->noise_prec[k * dd + k];
+            const double t = r * (prec * r);                                         /* covariance.py:19-22,54-55 */
+            acc = (k == 0) ? t : acc + t;
+        }
+        q[n] = acc;
+    }
+    const double logL = -0.5 * np_pairwise_sum(q, L->n_data);
+    double xx[YO_MAX_DIM];
+    for (int i = 0; i < d; i++) xx[i] = x[i] - L->prior_mean[i];
+    return logL + (-0.5 * quad_form(L->prior_prec, xx, d));
+}
+/* AEMLikelihood.query_log_likelihood (likelihood.py:126-131): a cached value is NOT invalidated
+ * when the error model changes */
+static double aem_query_coarse(const yo_problem *pb, chain_state *cs, const double *x)
+{
+    /* the cache stores logL; the prior term is deterministic, so caching the sum is equivalent */
+    int idx = lru_find(pb, cs, x);
+    if (idx >= 0) {
+        const double ll = cs->lru_ll[idx];
+        lru_touch(pb, cs, idx);
+        return ll;
+    }
+    const double lp = aem_coarse_logpost(pb, cs, x);
+    lru_add(pb, cs, x, lp);
+    return lp;
+}
+/* AdaptiveErrorModel._process_transition on an accepted fine step (aem.py:25-58) +
+ * AEMLikelihood.update_error_estimate (likelihood.py:147-155) + AEMNoise (noise.py:41-54) */
+static void aem_update(const yo_problem *pb, chain_state *cs, const double *P)
+{
+    const yo_level *Lc = &pb->level[0], *Lf = &pb->level[1];
+    const int d = pb->dim, dd = Lc->data_dim;
+    double Fc[YO_MAX_DATA], Ff[YO_MAX_DATA];
+    int idx = lru_find(pb, cs, P);                    /* query_model_evaluation: a hit moves the entry back */
+    if (idx >= 0) lru_touch(pb, cs, idx); else cs->aem_model_evals++;
+    linear_forward(Lc, d, P, Fc);
+    linear_forward(Lf, d, P, Ff);
+    cs->aem_n++;
+    for (int k = 0; k < dd; k++) {                    /* Welford, estimation.py:36-53 */
+        const double e = Ff[k] - Fc[k];
+        const double delta = e - cs->aem_mean[k];
+        cs->aem_mean[k] += delta / (double)cs->aem_n;
+        cs->aem_m2[k] += delta * (e - cs->aem_mean[k]);
+    }
+    if (cs->aem_n > pb->aem_min_data) {
+        double mv[YO_MAX_DATA], mn = INFINITY, mx = -INFINITY;
+        for (int k = 0; k < dd; k++) {
+            mv[k] = cs->aem_m2[k] / (double)(cs->aem_n - 1);
+            if (mv[k] < mn) mn = mv[k];
+            if (mv[k] > mx) mx = mv[k];
+        }
+        double scaling = 1.0;
+        if (pb->aem_heuristic) {                      /* noise.py:41-46 */
+            const double minVal = mn > 1e-6 ? mn : 1e-6;
+            scaling = 2. * mx / minVal;
+            if (scaling > 100.) scaling = 100.;
+        }
+        for (int k = 0; k < dd; k++) {
+            const double dataVar = 1.0 / Lc->noise_prec[k * dd + k];     /* covariance.py:33-34 */
+            cs->aem_prec[k] = 1.0 / (scaling * mv[k] + dataVar);         /* noise.py:51-53, covariance.py:37-38 */
+        }
+        cs->aem_have_noise = 1;
+    }
+}
+
+/* One AEM transition (two level): aem.py + mlda.py:100-110,146-154 with the coarse likelihood's
+ * cache semantics.  Returns 1 if accepted. */
+static int chain_step_aem(const yo_problem *pb, chain_state *cs, const noise_src *ns, int64_t n)
+{
+    const int d = pb->dim;
+    double z[YO_MAX_DIM], p[YO_MAX_DIM], s[YO_MAX_DIM];
+    welford_update(cs, d);
+    memcpy(s, cs->theta, sizeof(double) * d);
+    for (int j = 0; j < pb->J; j++) {
+        get_z(pb, ns, n, j, z);
+        propose(pb, cs->L, s, z, p);
+        if (param_equal(pb, p, s)) continue;
+        const double lpp = aem_query_coarse(pb, cs, p);      /* mrw.py:53: proposal first, then state */
+        const double lps = aem_query_coarse(pb, cs, s);
+        if (accept_rule(lpp - lps, get_uc(pb, ns, n, j))) memcpy(s, p, sizeof(double) * d);
+    }
+    if (param_equal(pb, s, cs->theta)) return 0;
+    /* mlda.py:148-152: pi_f(P) + pi_c(theta) - pi_c(P) - pi_f(theta), evaluated in this order */
+    const double lpf_s = yo_logpost(pb, 1, s, &cs->n_evals[1]);
+    const double lpc_t = aem_query_coarse(pb, cs, cs->theta);
+    const double lpc_s = aem_query_coarse(pb, cs, s);
+    const double delta = lpf_s + lpc_t - lpc_s - cs->lp[1];
+    if (accept_rule(delta, get_uf(ns, n))) {
+        aem_update(pb, cs, s);
+        memcpy(cs->theta, s, sizeof(double) * d);
+        cs->lp[1] = lpf_s;
+        cs->n_accept++;
+        return 1;
+    }
+    return 0;
+}
+
 static void chain_init(const yo_problem *pb, chain_state *cs, const double *theta0)
 {
     memset(cs, 0, sizeof(*cs));
@@ -393,6 +564,7 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
 {
     const int d = pb->dim;
     double z[YO_MAX_DIM], p[YO_MAX_DIM];
+    if (pb->aem) return chain_step_aem(pb, cs, ns, n);
     welford_update(cs, d);                               /* diagnostics.py:91-94 */
     if (pb->n_levels == 1) {
         if (pb->adaptive) am_update(pb, cs, (int64_t)ns->step0 + n);
@@ -443,8 +615,8 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
 int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
                     const double *theta0, const double *z, const double *u_c, const double *u_f,
                     double *traj, uint8_t *accepted, double *lp0, double *lp1,
-                    double *w_mean, double *w_var, int64_t *n_evals, int n_threads)
-{
+                    double *w_mean, double *w_var, int64_t *n_evals, int n_threads, double *aem_out)
+{   /* aem_out[nc, 2 + 2 data_dim]: error samples, coarse model evaluations, error mean, error variance */
     const int d = pb->dim, J = pb->J;
     if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 2) return -1;
     for (int l = 0; l < pb->n_levels; l++) if (pb->model != YO_GAUSS && pb->level[l].data_dim > YO_MAX_DATA) return -1;
@@ -470,6 +642,16 @@ int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
             if (w_var) w_var[c * d + i] = cs.w_n > 1 ? cs.w_m2[i] / (double)(cs.w_n - 1) : NAN;
         }
         ev0 += cs.n_evals[0]; ev1 += cs.n_evals[1];
+        if (aem_out && pb->aem) {
+            const int dd = pb->level[0].data_dim;
+            double *o = aem_out + (size_t)c * (2 + 2 * dd);
+            o[0] = (double)cs.aem_n;
+            o[1] = (double)cs.aem_model_evals;
+            for (int k = 0; k < dd; k++) {
+                o[2 + k] = cs.aem_mean[k];
+                o[2 + dd + k] = cs.aem_n > 1 ? cs.aem_m2[k] / (double)(cs.aem_n - 1) : 0.0;
+            }
+        }
     }
     if (n_evals) { n_evals[0] = ev0; n_evals[1] = ev1; }
     return 0;

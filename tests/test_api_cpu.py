@@ -14,7 +14,8 @@ from yagre_mcmc_b200.statistics import (IIDCovarianceMatrix, DiagonalCovarianceM
                                         GaussianTargetDensity2d, GaussianTargetDensity1d)
 from yagre_mcmc_b200.statistics.interface import DensityInterface
 from yagre_mcmc_b200.utility import Hierarchy, SharedComponent
-from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder
+from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder, AEMBuilder
+from yagre_mcmc_b200.statistics import AEMLikelihood, AEMNoise
 from yagre_mcmc_b200.chain.target import UnnormalisedPosterior
 from yagre_mcmc_b200.chain.lowering import lower_problem
 from yagre_mcmc_b200.parallel import shard_range, moments_from_stats
@@ -67,6 +68,35 @@ def test_pcn_builder_validation():
         b2.build_method()
     b2.stepSize = 0.7
     with pytest.raises(AssertionError):
+        b2.build_method()
+
+
+def test_aem_builder_validation():
+    """reference chain/method/aem.py:66-79, statistics/likelihood.py:99-100, statistics/noise.py:29-33."""
+    data = Data(np.zeros((3, 2)))
+    fm = ForwardModel(LinearModelSolver(np.eye(2), np.zeros(2)))
+    noise = CentredGaussianNoise(IIDCovarianceMatrix(2, 0.3))
+    with pytest.raises(ValueError, match="Smallest senisible data size for AEM is 2"):
+        AEMLikelihood(data, fm, noise, 1)
+    with pytest.raises(NotImplementedError, match="independent measurement noise"):
+        AEMLikelihood(data, fm, CentredGaussianNoise(DenseCovarianceMatrix(np.eye(2) + 0.1)), 5)
+    prior = Gaussian(ParameterVector(np.zeros(2)), IIDCovarianceMatrix(2, 1.))
+    plain = AdditiveGaussianNoiseLikelihood(data, fm, noise)
+    aem = AEMLikelihood(data, fm, noise, 10, True)
+    assert aem.device_aem() == dict(min_data=10, heuristic=True) and isinstance(aem.noiseModel, AEMNoise)
+    assert AEMNoise.scaling_heuristic(np.array([0.5, 0.01])) == 100 and AEMNoise.scaling_heuristic(np.array([0.2, 0.1])) == 4.0
+    b = AEMBuilder()
+    b.baseProposalCovariance = IIDCovarianceMatrix(2, 0.5)
+    b.subChainLengths = [5]
+    b.explicitTarget = GaussianTargetDensity2d(ParameterVector(np.zeros(2)), np.eye(2))
+    b.surrogateTargets = [b.explicitTarget]
+    with pytest.raises(NotImplementedError, match="only makes sense if the target emerges from a Bayesian model"):
+        b.build_method()
+    b2 = AEMBuilder()
+    b2.baseProposalCovariance = IIDCovarianceMatrix(2, 0.5)
+    b2.subChainLengths = [5]
+    b2.bayesModel = BayesianRegressionModelHierarchy(Hierarchy([aem, plain]), SharedComponent(prior, 2))
+    with pytest.raises(ValueError, match="Likelihood on level 1 is not adaptive"):
         b2.build_method()
 
 

@@ -13,7 +13,8 @@ from yagre_mcmc_b200.statistics import (IIDCovarianceMatrix, DiagonalCovarianceM
                                         BayesianRegressionModel, BayesianRegressionModelHierarchy,
                                         GaussianTargetDensity2d, GaussianTargetDensity1d)
 from yagre_mcmc_b200.utility import Hierarchy, SharedComponent
-from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder
+from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder, AEMBuilder
+from yagre_mcmc_b200.statistics import AEMLikelihood
 from yagre_mcmc_b200.chain.diagnostics import DummyDiagnostics, AcceptanceRateDiagnostics, FullDiagnostics
 from yagre_mcmc_b200.postprocessing.autocorrelation import integrated_autocorrelation, effective_sample_size
 
@@ -234,6 +235,39 @@ def test_linear_two_level_through_builders_matches_closed_form():
     # slow mixer (see tests/test_backend_gpu.py::test_c3_linear_posterior_moments): loose tolerances
     np.testing.assert_allclose(x.mean(0), mean, atol=0.03)
     np.testing.assert_allclose(np.cov(x.T), cov, rtol=0.15, atol=5e-3)
+
+
+def test_adaptive_error_model_through_builders():
+    """example_inference_linearModel_twoLevel.py:95-102,183-191: AEM on the C3 linear pair lifts the fine
+    acceptance rate (0.04 -> 0.35 in the reference's script) and still samples the fine posterior."""
+    meta, a = bp.linear_problem(True)
+    noise = CentredGaussianNoise(IIDCovarianceMatrix(2, 0.3))
+    prior = Gaussian(ParameterVector(a["L0_prior_mean"]), IIDCovarianceMatrix(2, 5.0))
+    lik = [AEMLikelihood(Data(a["L0_data"]), ForwardModel(LinearModelSolver(a[f"L{l}_G"], a[f"L{l}_b"])), noise, 100, True)
+           for l in range(2)]
+    b = AEMBuilder()
+    b.bayesModel = BayesianRegressionModelHierarchy(Hierarchy(lik), SharedComponent(prior, 2))
+    b.baseProposalCovariance = IIDCovarianceMatrix(2, 0.5)
+    b.subChainLengths = [5]
+    b.targetDiagnostics = FullDiagnostics()
+    b.nChains, b.seed, b.thin = 2048, 9, 50
+    mc = b.build_method()
+    mc.run(6001, ParameterVector(np.zeros(2)), verbose=False)
+    em = mc.error_model()
+    # a per-chain error model can also go wrong for an individual chain (a poor early estimate freezes it),
+    # exactly as a single reference chain can: judge the ensemble by its bulk
+    assert em["nData"].shape == (2048,) and np.median(em["nData"]) > 1000 and (em["nData"] > 200).mean() > 0.95
+    mean, cov = bp.linear_posterior('f')
+    # the error model estimates E[F_f - F_c] over the posterior: (G_f - G_c) mean + (b_f - b_c)
+    expect = (a["L1_G"] - a["L0_G"]) @ mean + (a["L1_b"] - a["L0_b"])
+    np.testing.assert_allclose(np.median(em["mean"], axis=0), expect, atol=0.05)
+    assert mc.diagnostics.global_acceptance_rate() > 0.2
+    good = em["nData"] > 200
+    x = np.asarray(mc.chain.trajectory)[60:][:, good].reshape(-1, 2)
+    np.testing.assert_allclose(x.mean(0), mean, atol=0.03)
+    np.testing.assert_allclose(np.cov(x.T), cov, rtol=0.15, atol=5e-3)
+    coarse, fine = mc.evaluation_counts()
+    assert coarse >= 5 * 2048 * 6000 * 0.99                    # J proposals per step + cache-miss re-evaluations
 
 
 def test_adaptive_metropolis_builder():

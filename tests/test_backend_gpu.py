@@ -25,7 +25,7 @@ def _replay(meta, arrays, th0, out, adaptive=None):
     z = out["z"].cpu().numpy().transpose(3, 0, 1, 2)
     u_c = np.nan_to_num(out["u_c"].cpu().numpy().transpose(2, 0, 1), nan=0.5)
     u_f = np.nan_to_num(out["u_f"].cpu().numpy().transpose(1, 0), nan=0.5)
-    return cport.run_injected(cport.Problem(meta, arrays, adaptive=adaptive), th0, z, u_c, u_f)
+    return cport.run_injected(cport.Problem(meta, arrays, adaptive=adaptive), th0, z, u_c, u_f)     # meta['aem'] is honoured
 
 
 CASES = {
@@ -252,6 +252,78 @@ def test_nonfinite_forward_output_is_rejected():
     ens = _ens(meta, arrays, 32)
     lp = ens.logpost(0, np.tile([6.0, 6.0], (32, 1))).cpu().numpy()
     assert np.all(np.isneginf(lp))
+
+
+# ------------------------------------------------------------------------------------------
+# adaptive error model (chain/method/aem.py)
+# ------------------------------------------------------------------------------------------
+
+def _aem_run(meta, a, **kw):
+    nc, ns = a["u_f"].shape
+    ens = _ens(meta, a, nc, aem=meta["aem"], **kw)
+    ens.set_state(a["theta0"])
+    inj = dict(z=np.ascontiguousarray(np.transpose(a["z"], (1, 2, 3, 0))),
+               u_c=np.ascontiguousarray(np.transpose(a["u_c"], (1, 2, 0))),
+               u_f=np.ascontiguousarray(np.transpose(a["u_f"], (1, 0))))
+    out = ens.run(ns, samples=True, accepted=True, inject=inj)
+    return ens, out
+
+
+@pytest.mark.parametrize("name", ["aem_linear", "aem_linear_noheuristic"])
+def test_adaptive_error_model_matches_reference_fixture(name):
+    """Same noise as the unmodified reference's AEM run: identical decisions and trajectory, the same
+    error-model state, and the same number of coarse model evaluations (= the LRU(3) cache of the
+    coarse likelihood, stale entries included, behaves like the reference's)."""
+    meta, a = load(name)
+    ens, out = _aem_run(meta, a)
+    acc = out["accepted"].cpu().numpy().T
+    assert int((acc != a["accepted"]).sum()) == 0
+    traj = out["samples"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(traj, a["traj"][:, 1:]).max() <= 1e-12
+    st = ens.state()
+    n = st["aem_n"].cpu().numpy()
+    assert np.array_equal(n, a["aem_n"])
+    np.testing.assert_allclose(st["aem_mean"].cpu().numpy().T, a["aem_mean"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(st["aem_m2"].cpu().numpy().T / (n[:, None] - 1), a["aem_var"], rtol=1e-10, atol=1e-14)
+    c = ens.counters()
+    assert c["coarse_evals"] == int(a["n_model_evals"][:, 0].sum())
+    assert c["accepted"] == int(a["accepted"].sum())
+
+
+def test_adaptive_error_model_philox_replay_and_resume():
+    from oracle import cport
+    meta, arrays = bp.linear_problem(True)
+    meta = dict(meta, aem=dict(min_data=8, heuristic=True))
+    nc, ns = 500, 300
+    th0 = np.zeros((nc, 2))
+    ens = _ens(meta, arrays, nc, seed=77, aem=meta["aem"])
+    ens.set_state(th0)
+    out = ens.run(ns, samples=True, accepted=True, record=True)
+    ref = _replay(meta, arrays, th0, out)
+    acc = out["accepted"].cpu().numpy().T
+    assert int((acc != ref["accepted"]).sum()) == 0
+    assert rel_err(out["samples"].cpu().numpy().transpose(2, 0, 1), ref["traj"][:, 1:]).max() <= 1e-12
+    st = ens.state()
+    assert np.array_equal(st["aem_n"].cpu().numpy(), ref["aem_n"])
+    np.testing.assert_allclose(st["aem_mean"].cpu().numpy().T, ref["aem_mean"], rtol=1e-9, atol=1e-13)
+    assert ens.counters()["coarse_evals"] == int(ref["aem_model_evals"].sum())
+    # the error model lifts the fine acceptance rate well above the plain two-level chain's (SURVEY 8f: 0.04 -> 0.35)
+    plain = _ens(bp.linear_problem(True)[0], arrays, nc, seed=77)
+    plain.set_state(th0)
+    plain.run(ns, samples=False)
+    assert acc[:, 150:].mean() > 2.0 * plain.counters()["accepted"] / (nc * ns)
+    # resume: 300 = 120 + save/load + 180, bit exact (cache and error model are part of the state)
+    b = _ens(meta, arrays, nc, seed=77, aem=meta["aem"])
+    b.set_state(th0)
+    first = b.run(120, samples=True)["samples"]
+    c = _ens(meta, arrays, nc, seed=77, aem=meta["aem"])
+    c.load_state(b.state())
+    second = c.run(180, samples=True)["samples"]
+    assert torch.equal(torch.cat([first, second]), out["samples"])
+    with pytest.raises(ValueError):
+        _ens(meta, arrays, 8, aem=dict(min_data=1))
+    with pytest.raises(NotImplementedError):
+        _ens(bp.lv_problem(True)[0], bp.lv_problem(True)[1], 8, aem=dict(min_data=5))
 
 
 # ------------------------------------------------------------------------------------------

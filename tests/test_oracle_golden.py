@@ -26,6 +26,21 @@ def test_chain_trajectory_matches_reference(name):
         np.testing.assert_allclose(out["welford_var"], a["welford_var"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["aem_linear", "aem_linear_noheuristic"])
+def test_adaptive_error_model_matches_reference(name):
+    """AEM (chain/method/aem.py): trajectory, decisions, the error model's Welford state and even the
+    number of coarse model evaluations (which depends on the LRU(3) cache behaviour, memoisation.py:76-149)
+    equal the unmodified reference's."""
+    meta, a = load(name)
+    out = cport.run_injected(cport.Problem(meta, a), a["theta0"], a["z"], a["u_c"], a["u_f"])
+    assert np.array_equal(out["accepted"], a["accepted"])
+    assert rel_err(out["traj"], a["traj"]).max() <= 1e-13
+    assert np.array_equal(out["aem_n"], a["aem_n"])
+    np.testing.assert_allclose(out["aem_mean"], a["aem_mean"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(out["aem_var"], a["aem_var"], rtol=1e-12, atol=1e-15)
+    assert np.array_equal(out["aem_model_evals"], a["n_model_evals"][:, 0])
+
+
 def test_rng_call_order_of_reference_is_what_the_restatement_assumes():
     """(N u)*J then U only if the sub-chain moved."""
     meta, a = load("mlda_gauss2d")

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyagre_b200.so")
 
-YG_ABI_VERSION = 2
+YG_ABI_VERSION = 3
 YG_MAX_DIM = 8
 YG_MAX_DATA_DIM = 8
 YG_BIG_MAX_DIM = 64
@@ -51,7 +51,8 @@ class YgConfig(C.Structure):
                 ("am_refresh", C.c_int32), ("_pad0", C.c_int32),
                 ("am_eps", C.c_double), ("am_scale", C.c_double),
                 ("blocks_per_sm", C.c_int32), ("threads_per_block", C.c_int32),
-                ("rk4_segment", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("rk4_segment", C.c_int32), ("aem", C.c_int32), ("aem_min_data", C.c_int32),
+                ("aem_heuristic", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class YgNoise(C.Structure):
@@ -66,7 +67,9 @@ class YgOutputs(C.Structure):
 class YgState(C.Structure):
     _fields_ = [("theta_dev", C.c_void_p), ("logpost_dev", C.c_void_p), ("n_accept_dev", C.c_void_p),
                 ("w_mean_dev", C.c_void_p), ("w_m2_dev", C.c_void_p), ("prop_L_dev", C.c_void_p),
-                ("am_mean_dev", C.c_void_p), ("am_m2_dev", C.c_void_p)]
+                ("am_mean_dev", C.c_void_p), ("am_m2_dev", C.c_void_p),
+                ("aem_n_dev", C.c_void_p), ("aem_mean_dev", C.c_void_p), ("aem_m2_dev", C.c_void_p),
+                ("aem_cache_dev", C.c_void_p)]
 
 
 # every symbol include/yagre_b200.h declares: (restype, argtypes)

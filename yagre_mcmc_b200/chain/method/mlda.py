@@ -47,7 +47,7 @@ class MLDA(MetropolisHastings):
 
     def __init__(self, targetDensity, surrogateDensities, baseProposalCov, nSteps, targetDiagnostics,
                  surrogateDiagnosticsList, nChains=1, seed=0, device=None, thin=1, storeTrajectory=True,
-                 launch=None, equality='exact'):
+                 launch=None, equality='exact', aem=None):
         if len(surrogateDensities) != 1:
             raise NotImplementedError(
                 f"{len(surrogateDensities)} surrogates: only two-level delayed acceptance runs on the device")
@@ -55,7 +55,7 @@ class MLDA(MetropolisHastings):
                                 subChainLength=nSteps[0], equality=equality)
         proposal = MLDAProposal(surrogateDensities, baseProposalCov, nSteps)
         super().__init__(targetDensity, proposal, targetDiagnostics, lowered, nChains=nChains, seed=seed,
-                         device=device, thin=thin, storeTrajectory=storeTrajectory, launch=launch)
+                         device=device, thin=thin, storeTrajectory=storeTrajectory, launch=launch, aem=aem)
         self._surrogateDiagnostics = surrogateDiagnosticsList
         for lvl, t in enumerate([surrogateDensities[0], targetDensity]):
             if isinstance(t, UnnormalisedPosterior):
@@ -170,11 +170,14 @@ class MLDABuilder(ChainBuilder):
         posts = [UnnormalisedPosterior(self._bayesModel.level(k).likelihood, self._bayesModel.level(k).prior)
                  for k in range(n)]
         self.create_diagnostics(n - 1)
-        return MLDA(posts[-1], posts[:-1], self._basePropCov, self._nSteps, self._tgtDgnst,
-                    self._surrDgnstList, equality=self._stateEquality or 'exact', **self._common())
+        return self.build_mlda(posts[-1], posts[:-1], self._basePropCov, self._nSteps, self._tgtDgnst,
+                               self._surrDgnstList, equality=self._stateEquality or 'exact', **self._common())
 
     def build_from_target(self):
         self.create_diagnostics(len(self._surrTgts))
-        return MLDA(self._explicitTarget, list(self._surrTgts), self._basePropCov, self._nSteps,
-                    self._tgtDgnst, self._surrDgnstList, equality=self._stateEquality or 'exact',
-                    **self._common())
+        return self.build_mlda(self._explicitTarget, list(self._surrTgts), self._basePropCov, self._nSteps,
+                               self._tgtDgnst, self._surrDgnstList, equality=self._stateEquality or 'exact',
+                               **self._common())
+
+    def build_mlda(self, tgtPost, surPost, bpc, nS, tgtD, surD, **kw):      # reference mlda.py:337-338
+        return MLDA(tgtPost, surPost, bpc, nS, tgtD, surD, **kw)

@@ -29,7 +29,7 @@ from ..parallel import shard_range     # contiguous chain-id range of a rank: [r
 class MetropolisHastings:
 
     def __init__(self, targetDensity, proposalMethod, diagnostics, lowered, nChains=1, seed=0,
-                 device=None, adaptive=None, thin=1, storeTrajectory=True, launch=None):
+                 device=None, adaptive=None, thin=1, storeTrajectory=True, launch=None, aem=None):
         self._tgtDensity = targetDensity
         self._proposalMethod = proposalMethod
         self._diagnostics = diagnostics
@@ -49,7 +49,7 @@ class MetropolisHastings:
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self._ensemble = ChainEnsemble(lowered, self._nLocal, device=device, seed=self._seed,
-                                       chain_offset=self._offset, adaptive=adaptive, **(launch or {}))
+                                       chain_offset=self._offset, adaptive=adaptive, aem=aem, **(launch or {}))
         self._last = None
 
     # ---- reference surface ------------------------------------------------------------------

@@ -80,6 +80,13 @@ RunArgs make_args(yg_ensemble *e)
     a.am_collect = e->cfg.am_collection_steps;
     a.am_eps = e->cfg.am_eps;
     a.am_scale = e->cfg.am_scale > 0.0 ? e->cfg.am_scale : 2.4 * 2.4 / (double)e->cfg.dim;
+    a.aem = e->cfg.aem;
+    a.aem_min_data = e->cfg.aem_min_data;
+    a.aem_heuristic = e->cfg.aem_heuristic;
+    a.aem_n = e->aem_n;
+    a.aem_mean = e->aem_mean;
+    a.aem_m2 = e->aem_m2;
+    a.aem_cache = e->aem_cache;
     a.counters = e->counters;
     return a;
 }
@@ -241,6 +248,16 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
         yg_set_error("adaptive Metropolis: single level, dim >= 2, Gaussian/linear models only");
         return YG_ERR_UNSUPPORTED;   // dim == 1: chain/adaptive.py:41-43 refuses scalar chains too
     }
+    if (cfg->aem) {
+        if (cfg->n_levels != 2 || cfg->model != YG_MODEL_LINEAR || cfg->adaptive || cfg->dim > YG_MAX_DIM) {
+            yg_set_error("adaptive error model: two levels, linear model (dim <= %d), no adaptive proposal", YG_MAX_DIM);
+            return YG_ERR_UNSUPPORTED;   // aem.py:72-75: only defined for a hierarchy of Bayesian models
+        }
+        if (cfg->aem_min_data < 2) {
+            yg_set_error("Smallest senisible data size for AEM is 2.");      // likelihood.py:99-100
+            return YG_ERR_INVALID;
+        }
+    }
     if (cfg->eq_mode == YG_EQ_ISCLOSE && cfg->dim != 1) {
         yg_set_error("isclose equality is the ScalarParameter rule (dim must be 1)");
         return YG_ERR_INVALID;
@@ -291,6 +308,10 @@ extern "C" int yg_destroy(yg_ensemble *e)
     cudaFree(e->am_mean);
     cudaFree(e->am_m2);
     cudaFree(e->prop_L);
+    cudaFree(e->aem_n);
+    cudaFree(e->aem_mean);
+    cudaFree(e->aem_m2);
+    cudaFree(e->aem_cache);
     cudaFree(e->n_accept);
     cudaFree(e->counters);
     cudaFree(e->pool_partials);
@@ -419,6 +440,27 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
     YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     e->h_problem.swap(blob);
     e->problem_set = true;
+    if (e->cfg.aem) {
+        const yg_level &Lc = pb->level[0], &Lf = pb->level[1];
+        if (Lc.data_dim != Lf.data_dim || pb->proposal != YG_PROPOSAL_MRW) {
+            yg_set_error("adaptive error model: both levels must share the data dimension (MRW proposal)");
+            return YG_ERR_INVALID;
+        }
+        for (int i = 0; i < Lc.data_dim; i++)
+            for (int j = 0; j < Lc.data_dim; j++)
+                if (i != j && Lc.noise_prec[i * Lc.data_dim + j] != 0.0) {
+                    // noise.py:29-33
+                    yg_set_error("Currently, AEM is only implemented for independent measurement noise.");
+                    return YG_ERR_UNSUPPORTED;
+                }
+        const size_t n = (size_t)e->cfg.n_chains, dd = (size_t)Lc.data_dim;
+        cudaFree(e->aem_n); cudaFree(e->aem_mean); cudaFree(e->aem_m2); cudaFree(e->aem_cache);
+        e->aem_n = nullptr; e->aem_mean = e->aem_m2 = e->aem_cache = nullptr;
+        e->aem_data_dim = (int)dd;
+        if ((rc = dev_alloc(&e->aem_n, n)) || (rc = dev_alloc(&e->aem_mean, dd * n)) ||
+            (rc = dev_alloc(&e->aem_m2, dd * n)) || (rc = dev_alloc(&e->aem_cache, (size_t)(3 * (d + 1) + 1) * n)))
+            return rc;
+    }
     return YG_OK;
 }
 
@@ -444,6 +486,12 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
         broadcast_L_kernel<<<(int)std::min<size_t>((n + 127) / 128, 2048), 128, 0, st>>>(e->d_problem, e->prop_L,
                                                                                       (int64_t)n);
         YG_CUDA_CHECK(cudaGetLastError());
+    }
+    if (e->cfg.aem) {       // empty cache, no error realisations yet
+        YG_CUDA_CHECK(cudaMemsetAsync(e->aem_n, 0, sizeof(unsigned long long) * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->aem_mean, 0, sizeof(double) * (size_t)e->aem_data_dim * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->aem_m2, 0, sizeof(double) * (size_t)e->aem_data_dim * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->aem_cache, 0, sizeof(double) * (3 * (d + 1) + 1) * n, st));
     }
     for (int l = 0; l < e->cfg.n_levels; l++) {
         rc = e->big ? yg_launch_logpost_big(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st)
@@ -533,6 +581,17 @@ extern "C" int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream)
         if (dst->am_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->am_mean_dev, e->am_mean, 8 * d * n, k, st));
         if (dst->am_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->am_m2_dev, e->am_m2, 8 * d * d * n, k, st));
     }
+    if (dst->aem_n_dev || dst->aem_mean_dev || dst->aem_m2_dev || dst->aem_cache_dev) {
+        if (!e->cfg.aem) {
+            yg_set_error("aem_*_dev are per-chain state of adaptive-error-model ensembles only");
+            return YG_ERR_INVALID;
+        }
+        const size_t dd = (size_t)e->aem_data_dim;
+        if (dst->aem_n_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->aem_n_dev, e->aem_n, 8 * n, k, st));
+        if (dst->aem_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->aem_mean_dev, e->aem_mean, 8 * dd * n, k, st));
+        if (dst->aem_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->aem_m2_dev, e->aem_m2, 8 * dd * n, k, st));
+        if (dst->aem_cache_dev) YG_CUDA_CHECK(cudaMemcpyAsync(dst->aem_cache_dev, e->aem_cache, 8 * (3 * (d + 1) + 1) * n, k, st));
+    }
     return YG_OK;
 }
 
@@ -559,6 +618,13 @@ extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_i
         YG_CUDA_CHECK(cudaMemcpyAsync(e->am_mean, src->am_mean_dev, 8 * d * n, k, st));
     if (src->am_m2_dev && e->cfg.adaptive)
         YG_CUDA_CHECK(cudaMemcpyAsync(e->am_m2, src->am_m2_dev, 8 * d * d * n, k, st));
+    if (e->cfg.aem) {
+        const size_t dd = (size_t)e->aem_data_dim;
+        if (src->aem_n_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->aem_n, src->aem_n_dev, 8 * n, k, st));
+        if (src->aem_mean_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->aem_mean, src->aem_mean_dev, 8 * dd * n, k, st));
+        if (src->aem_m2_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->aem_m2, src->aem_m2_dev, 8 * dd * n, k, st));
+        if (src->aem_cache_dev) YG_CUDA_CHECK(cudaMemcpyAsync(e->aem_cache, src->aem_cache_dev, 8 * (3 * (d + 1) + 1) * n, k, st));
+    }
     e->step_index = step_index;
     e->welford_n = welford_n;
     e->state_set = true;

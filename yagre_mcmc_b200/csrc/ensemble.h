@@ -23,6 +23,11 @@ struct RunArgs {
     int32_t adaptive, am_refresh;
     int64_t am_idle, am_collect;
     double am_eps, am_scale;
+    // adaptive error model (generic kernel, two level, linear model)
+    int32_t aem, aem_min_data, aem_heuristic, _pad_aem;
+    unsigned long long *aem_n;      // [n]
+    double *aem_mean, *aem_m2;      // [data_dim, n]
+    double *aem_cache;              // [3 (d + 1) + 1, n]
     // outputs
     double *samples;                // [n_steps/thin, d, n]
     uint8_t *accepted;              // [n_steps, n]
@@ -47,6 +52,9 @@ struct yg_ensemble {
     DevProblemHeader *d_problem = nullptr;
     double *theta = nullptr, *logpost = nullptr, *w_mean = nullptr, *w_m2 = nullptr;
     double *am_mean = nullptr, *am_m2 = nullptr, *prop_L = nullptr;
+    unsigned long long *aem_n = nullptr;
+    double *aem_mean = nullptr, *aem_m2 = nullptr, *aem_cache = nullptr;
+    int aem_data_dim = 0;
     unsigned long long *n_accept = nullptr, *counters = nullptr;
     double *pool_partials = nullptr;   // [POOL_PARTS][yg_pooled_len(d)] scratch of yg_pooled_stats
     int64_t step_index = 0, welford_n = 0;

@@ -404,6 +404,390 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adaptive error model (two-level delayed acceptance on the linear model): reference
+// chain/method/aem.py:25-58, statistics/likelihood.py:90-155, statistics/noise.py:25-61,
+// utility/memoisation.py:76-149.  One chain per thread.  Per chain: Welford of F_fine - F_coarse
+// on accepted fine steps; the coarse residual is shifted by the error mean once min_data errors
+// were seen; the noise variance is inflated from min_data + 1 errors on; and the coarse
+// likelihood's LRU(3) cache is reproduced entry for entry, because the reference does NOT
+// invalidate cached log-likelihoods when the error model changes: which value a chain sees for
+// pi_c(state) depends on whether the state is still among the last three parameters queried.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct Lru3 {
+    double key[3][D], val[3];
+    int n;
+};
+
+template <int D>
+YG_DEVFN int lru_find(const Lru3<D> &c, const double (&x)[D], int d)
+{
+    int idx = -1;
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+        bool eq = i < c.n;
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            if (k < d) eq = eq && (c.key[i][k] == x[k]);            // parameter/vector.py:37-45
+        if (eq) idx = i;
+    }
+    return idx;
+}
+
+// AEMCache._move_to_back (memoisation.py:95-100): bubble entry idx to the newest position
+template <int D>
+YG_DEVFN void lru_touch(Lru3<D> &c, int idx)
+{
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (i >= idx && i + 1 < c.n) {
+#pragma unroll
+            for (int k = 0; k < D; k++) { const double t = c.key[i][k]; c.key[i][k] = c.key[i + 1][k]; c.key[i + 1][k] = t; }
+            const double t = c.val[i]; c.val[i] = c.val[i + 1]; c.val[i + 1] = t;
+        }
+    }
+}
+
+// AEMCache.add (memoisation.py:102-116): evict the oldest of three, append
+template <int D>
+YG_DEVFN void lru_add(Lru3<D> &c, const double (&x)[D], double v)
+{
+    if (c.n >= 3) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+#pragma unroll
+            for (int k = 0; k < D; k++) c.key[i][k] = c.key[i + 1][k];
+            c.val[i] = c.val[i + 1];
+        }
+        c.n = 2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (i == c.n) {
+#pragma unroll
+            for (int k = 0; k < D; k++) c.key[i][k] = x[k];
+            c.val[i] = v;
+        }
+    }
+    c.n++;
+}
+
+template <int D, int DD>
+__global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_blob(smem_raw, a.problem, a.problem_bytes);
+    const DevProblemHeader *pb = reinterpret_cast<const DevProblemHeader *>(smem_raw);
+    const int d = pb->dim, J = pb->J;
+    const DevLevel &Lc = pb->lvl[0], &Lf = pb->lvl[1];
+    const int dd = Lc.data_dim, nD = Lc.n_data;
+    const double *data = dev_tail(pb) + Lc.data_off;
+    const int64_t N = a.n_chains;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < N; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t gid = (uint64_t)(a.chain_offset + g);
+        double th[D], wm[D], w2[D][D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            th[i] = (i < d) ? a.theta[i * N + g] : 0.0;
+            wm[i] = (i < d) ? a.w_mean[i * N + g] : 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) w2[i][j] = (i < d && j < d) ? a.w_m2[(i * d + j) * N + g] : 0.0;
+        }
+        double lp0 = a.logpost[g], lp1 = a.logpost[N + g];
+        unsigned long long nacc = a.n_accept[g];
+        // ---- error model + cache state -----------------------------------------------------------
+        unsigned long long en = a.aem_n[g];
+        double em[DD], e2[DD], eprec[DD];
+        bool have_noise = false;
+#pragma unroll
+        for (int k = 0; k < DD; k++) {
+            em[k] = (k < dd) ? a.aem_mean[k * N + g] : 0.0;
+            e2[k] = (k < dd) ? a.aem_m2[k * N + g] : 0.0;
+            eprec[k] = 0.0;
+        }
+        Lru3<D> cache;
+        {
+            const int stride = d + 1;
+            cache.n = (int)a.aem_cache[(int64_t)(3 * stride) * N + g];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int k = 0; k < D; k++) cache.key[i][k] = (k < d) ? a.aem_cache[(int64_t)(i * stride + k) * N + g] : 0.0;
+                cache.val[i] = a.aem_cache[(int64_t)(i * stride + d) * N + g];
+            }
+        }
+        // noise.py:41-54 (+ covariance.py:33-38): precision of the inflated noise from the current moments
+        auto refresh_noise = [&]() {
+            if (en > (unsigned long long)a.aem_min_data) {
+                double mv[DD], mn = CUDART_INF, mx = -CUDART_INF;
+#pragma unroll
+                for (int k = 0; k < DD; k++) {
+                    mv[k] = (k < dd) ? e2[k] / (double)(en - 1ull) : 0.0;
+                    if (k < dd) { mn = fmin(mn, mv[k]); mx = fmax(mx, mv[k]); }
+                }
+                double scaling = 1.0;
+                if (a.aem_heuristic) {
+                    const double minVal = mn > 1e-6 ? mn : 1e-6;
+                    scaling = 2.0 * mx / minVal;
+                    if (scaling > 100.0) scaling = 100.0;
+                }
+#pragma unroll
+                for (int k = 0; k < DD; k++)
+                    if (k < dd) eprec[k] = 1.0 / (scaling * mv[k] + 1.0 / Lc.noise_prec[k * dd + k]);
+                have_noise = true;
+            }
+        };
+        refresh_noise();
+        auto forward = [&](const DevLevel &Lv, const double (&x)[D], double (&F)[DD]) {
+#pragma unroll
+            for (int k = 0; k < DD; k++) {
+                double acc = 0.0;
+                if (k < dd) {
+#pragma unroll
+                    for (int j = 0; j < D; j++)
+                        if (j < d) acc = (j == 0) ? Lv.G[k * d] * x[0] : fma(Lv.G[k * d + j], x[j], acc);
+                    acc += Lv.b[k];
+                }
+                F[k] = acc;
+            }
+        };
+        // AEMLikelihood.compute_log_likelihood (likelihood.py:74-84,140-145) + prior (target.py:19-22)
+        auto coarse_logpost = [&](const double (&x)[D]) {
+            double F[DD];
+            forward(Lc, x, F);
+            cnt_ev0++;
+            const bool shift = en >= (unsigned long long)a.aem_min_data;
+            const double sum = np_stream_sum(nD, [&](int n) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < DD; k++) {
+                    if (k < dd) {
+                        double r = F[k] - data[n * dd + k];
+                        if (shift) r = r + em[k];
+                        const double prec = have_noise ? eprec[k] : Lc.noise_prec[k * dd + k];
+                        acc = (k == 0) ? r * (prec * r) : fma(r, prec * r, acc);
+                    }
+                }
+                return acc;
+            });
+            double xx[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) xx[i] = (i < d) ? x[i] - Lc.prior_mean[i] : 0.0;
+            return -0.5 * sum + (-0.5 * quad_form<D>(Lc.prior_prec, d, xx, d));
+        };
+        // AEMLikelihood.query_log_likelihood (likelihood.py:126-131)
+        auto query_coarse = [&](const double (&x)[D]) {
+            const int idx = lru_find<D>(cache, x, d);
+            if (idx >= 0) {
+                const double v = (idx == 0) ? cache.val[0] : (idx == 1 ? cache.val[1] : cache.val[2]);
+                lru_touch<D>(cache, idx);
+                return v;
+            }
+            const double v = coarse_logpost(x);
+            lru_add<D>(cache, x, v);
+            return v;
+        };
+        auto propose = [&](const double (&s)[D], int64_t n, int j, uint64_t step, double (&p)[D]) {
+            double z[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) z[i] = 0.0;
+            if (a.noise_mode == YG_NOISE_INJECT) {
+#pragma unroll
+                for (int i = 0; i < D; i++) z[i] = (i < d) ? a.z[((n * J + j) * d + i) * N + g] : 0.0;
+            } else {
+#pragma unroll
+                for (int b = 0; b < (D + 1) / 2; b++) {
+                    if (2 * b < d) {
+                        double z0, z1;
+                        philox_normal_pair(a.seed, gid, step, (uint32_t)j, (uint32_t)b, z0, z1);
+                        z[2 * b] = z0;
+                        if (2 * b + 1 < D) z[2 * b + 1] = z1;
+                    }
+                }
+                if (a.noise_mode == YG_NOISE_RECORD) {
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                        if (i < d) a.z[((n * J + j) * d + i) * N + g] = z[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double acc = 0.0;
+                bool first = true;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    if (k <= i && i < d) {
+                        const double l = pb->prop_L[i * d + k];
+                        if (l != 0.0 || k == i) {
+                            const double t = __dmul_rn(l, z[k]);
+                            acc = first ? t : __dadd_rn(acc, t);
+                            first = false;
+                        }
+                    }
+                }
+                p[i] = (i < d) ? __dadd_rn(s[i], acc) : 0.0;
+            }
+        };
+        auto equal = [&](const double (&p)[D], const double (&s)[D]) {
+            bool eq = true;
+#pragma unroll
+            for (int i = 0; i < D; i++)
+                if (i < d) eq = eq && (p[i] == s[i]);
+            return eq;
+        };
+
+        for (int64_t n = 0; n < a.n_steps; n++) {
+            const uint64_t step = (uint64_t)(a.step0 + n);
+            {   // diagnostics Welford of the pre-transition state (diagnostics.py:91-94)
+                const double wn = (double)(a.welford_n0 + n + 1);
+                double dl[D], e[D];
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    dl[i] = th[i] - wm[i];
+                    wm[i] += dl[i] / wn;
+                    e[i] = th[i] - wm[i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; i++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) w2[i][j] += dl[i] * e[j];
+            }
+            bool accepted = false;
+            double s[D], p[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) s[i] = th[i];
+            for (int j = 0; j < J; j++) {                               // coarse sub-chain, mlda.py:100-110
+                propose(s, n, j, step, p);
+                if (equal(p, s)) continue;
+                const double lpp = query_coarse(p);                     // mrw.py:53: proposal first, then state
+                const double lps = query_coarse(s);
+                double u;
+                const int64_t ui = (n * J + j) * N + g;
+                if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
+                else {
+                    u = philox_uniform(a.seed, gid, step, (uint32_t)j);
+                    if (a.noise_mode == YG_NOISE_RECORD) a.u_c[ui] = u;
+                }
+                if (accept_rule(lpp - lps, u)) {
+#pragma unroll
+                    for (int i = 0; i < D; i++) s[i] = p[i];
+                }
+            }
+            if (!equal(s, th)) {
+                // mlda.py:148-152: pi_f(P) + pi_c(theta) - pi_c(P) - pi_f(theta), evaluated in this order
+                const double lpf_s = logpost_any<D, DD>(pb, 1, s);
+                cnt_ev1++;
+                const double lpc_t = query_coarse(th);
+                const double lpc_s = query_coarse(s);
+                double u;
+                if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
+                else {
+                    u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                    if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
+                }
+                const double delta = lpf_s + lpc_t - lpc_s - lp1;
+                if (accept_rule(delta, u)) {
+                    // aem.py:44-56 + likelihood.py:147-155: feed F_f(P) - F_c(P) to the coarse error model
+                    const int idx = lru_find<D>(cache, s, d);           // query_model_evaluation: a hit moves the entry back
+                    if (idx >= 0) lru_touch<D>(cache, idx); else cnt_ev0++;
+                    double Fc[DD], Ff[DD];
+                    forward(Lc, s, Fc);
+                    forward(Lf, s, Ff);
+                    en += 1ull;
+#pragma unroll
+                    for (int k = 0; k < DD; k++) {
+                        if (k < dd) {                                    // estimation.py:36-53
+                            const double e = Ff[k] - Fc[k];
+                            const double dl = e - em[k];
+                            em[k] += dl / (double)en;
+                            e2[k] += dl * (e - em[k]);
+                        }
+                    }
+                    refresh_noise();
+#pragma unroll
+                    for (int i = 0; i < D; i++) th[i] = s[i];
+                    lp0 = lpc_s;
+                    lp1 = lpf_s;
+                    accepted = true;
+                }
+            }
+            if (accepted) { nacc++; cnt_acc++; }
+            cnt_tr++;
+            if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+            if ((n + 1) % a.thin == 0) {
+                const int64_t o = (n + 1) / a.thin - 1;
+                if (a.samples) {
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                        if (i < d) a.samples[(o * d + i) * N + g] = th[i];
+                }
+                if (a.lp_out) {
+                    a.lp_out[(o * 2) * N + g] = lp0;        // coarse value as last evaluated (may be stale, see above)
+                    a.lp_out[(o * 2 + 1) * N + g] = lp1;
+                }
+            }
+        }
+        // ---- store chain state ---------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            if (i < d) {
+                a.theta[i * N + g] = th[i];
+                a.w_mean[i * N + g] = wm[i];
+#pragma unroll
+                for (int j = 0; j < D; j++)
+                    if (j < d) a.w_m2[(i * d + j) * N + g] = w2[i][j];
+            }
+        }
+        a.logpost[g] = lp0;
+        a.logpost[N + g] = lp1;
+        a.n_accept[g] = nacc;
+        a.aem_n[g] = en;
+#pragma unroll
+        for (int k = 0; k < DD; k++) {
+            if (k < dd) { a.aem_mean[k * N + g] = em[k]; a.aem_m2[k * N + g] = e2[k]; }
+        }
+        {
+            const int stride = d + 1;
+            a.aem_cache[(int64_t)(3 * stride) * N + g] = (double)cache.n;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int k = 0; k < D; k++)
+                    if (k < d) a.aem_cache[(int64_t)(i * stride + k) * N + g] = cache.key[i][k];
+                a.aem_cache[(int64_t)(i * stride + d) * N + g] = cache.val[i];
+            }
+        }
+    }
+    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
+    }
+}
+
+template <int D, int DD>
+int launch_aem_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
+{
+    const int threads = 128;
+    const int64_t want = (a.n_chains + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
+    const size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
+    auto kern = aem_mh_kernel<D, DD>;
+    YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+    YG_CUDA_CHECK(cudaGetLastError());
+    e->last_grid = grid;
+    e->last_block = threads;
+    e->last_smem = (int)smem;
+    e->launches += 1;
+    return YG_OK;
+}
+
 int cap_of(int n)
 {
     return n <= 2 ? 2 : (n <= 4 ? 4 : 8);
@@ -463,7 +847,11 @@ int yg_launch_generic(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
     const int cd = cap_of(hp->dim);
     const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim)));
-    YG_DISPATCH(launch_generic_t, e, a, st)
+    if (a.aem) {
+        YG_DISPATCH(launch_aem_t, e, a, st)
+    } else {
+        YG_DISPATCH(launch_generic_t, e, a, st)
+    }
     yg_set_error("unsupported dimensions d=%d data_dim=%d", hp->dim, hp->lvl[0].data_dim);
     return YG_ERR_UNSUPPORTED;
 }

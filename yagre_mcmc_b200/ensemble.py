@@ -81,7 +81,7 @@ class ChainEnsemble:
     """n_chains independent chains of one problem on one device."""
 
     def __init__(self, problem, n_chains, device=0, seed=0, chain_offset=0,
-                 adaptive=None, blocks_per_sm=0, threads_per_block=0, rk4_segment=0):
+                 adaptive=None, blocks_per_sm=0, threads_per_block=0, rk4_segment=0, aem=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.BackendUnavailable("no CUDA device visible: the batched-chain backend has no CPU fallback")
@@ -105,6 +105,12 @@ class ChainEnsemble:
         cfg.blocks_per_sm = int(blocks_per_sm)
         cfg.threads_per_block = int(threads_per_block)
         cfg.rk4_segment = int(rk4_segment)
+        self.aem = None
+        if aem:             # adaptive error model: dict(min_data=..., heuristic=...)
+            cfg.aem = 1
+            cfg.aem_min_data = int(aem['min_data'])
+            cfg.aem_heuristic = int(bool(aem.get('heuristic', False)))
+            self.aem = dict(aem)
         if adaptive:
             cfg.adaptive = 1
             cfg.am_idle_steps = int(adaptive.get('idle', 0))
@@ -212,6 +218,13 @@ class ChainEnsemble:
             r['prop_L'], r['am_mean'], r['am_m2'] = self._empty(d, d, n), self._empty(d, n), self._empty(d, d, n)
             st.prop_L_dev, st.am_mean_dev, st.am_m2_dev = (r['prop_L'].data_ptr(), r['am_mean'].data_ptr(),
                                                            r['am_m2'].data_ptr())
+        if self.cfg.aem:
+            dd = int(np.asarray(self.problem.arrays['L0_data']).shape[1])
+            r['aem_n'] = self._empty(n, dtype=torch.int64)
+            r['aem_mean'], r['aem_m2'] = self._empty(dd, n), self._empty(dd, n)
+            r['aem_cache'] = self._empty(3 * (d + 1) + 1, n)
+            st.aem_n_dev, st.aem_mean_dev = r['aem_n'].data_ptr(), r['aem_mean'].data_ptr()
+            st.aem_m2_dev, st.aem_cache_dev = r['aem_m2'].data_ptr(), r['aem_cache'].data_ptr()
         with torch.cuda.device(self.device):
             check(self.lib.yg_get_state(self._h, C.byref(st), self._stream()))
         c = self.counters()
@@ -221,7 +234,8 @@ class ChainEnsemble:
     def load_state(self, r):
         st = YgState()
         keep = {k: r[k].to(self.device).contiguous() for k in
-                ('theta', 'logpost', 'n_accept', 'w_mean', 'w_m2', 'prop_L', 'am_mean', 'am_m2') if k in r}
+                ('theta', 'logpost', 'n_accept', 'w_mean', 'w_m2', 'prop_L', 'am_mean', 'am_m2',
+                 'aem_n', 'aem_mean', 'aem_m2', 'aem_cache') if k in r}
         st.theta_dev, st.logpost_dev = keep['theta'].data_ptr(), keep['logpost'].data_ptr()
         if 'n_accept' in keep:
             st.n_accept_dev = keep['n_accept'].data_ptr()
@@ -231,6 +245,9 @@ class ChainEnsemble:
             st.prop_L_dev = keep['prop_L'].data_ptr()
         if 'am_mean' in keep and 'am_m2' in keep and self.cfg.adaptive:
             st.am_mean_dev, st.am_m2_dev = keep['am_mean'].data_ptr(), keep['am_m2'].data_ptr()
+        if self.cfg.aem and all(k in keep for k in ('aem_n', 'aem_mean', 'aem_m2', 'aem_cache')):
+            st.aem_n_dev, st.aem_mean_dev = keep['aem_n'].data_ptr(), keep['aem_mean'].data_ptr()
+            st.aem_m2_dev, st.aem_cache_dev = keep['aem_m2'].data_ptr(), keep['aem_cache'].data_ptr()
         with torch.cuda.device(self.device):
             check(self.lib.yg_load_state(self._h, C.byref(st), int(r.get('step_index', 0)),
                                          int(r.get('welford_n', 0)), self._stream()))
