@@ -157,6 +157,8 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -228,7 +230,12 @@ def run_gpu_arm(args):
     peak = fp64_peak_tflops(local, 30.0)
     achieved = flops / n_gpus / (total_ms_max * 1e-3) / 1e12          # per GPU
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full capture of this
+                # command, profiles/r01_lv_mh_kernel_ncu_full.csv): 5.87 MB + 0.30 MB; the algorithmic state
+                # traffic is 96 B per chain per launch = 6.3 MB at 65,536 chains (written state stays in L2)
+                "traffic": 6.17e6 if (args.chains == CHAINS_PER_GPU) else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_lv_mh_kernel_ncu_full.csv",
+                "algorithmic_bytes_per_launch": 96.0 * args.chains,
                 "kernel": "lv_mh_kernel<true>", "launch_ms": total_ms_max / args.steps,
                 "algorithmic_flop_per_launch": flops / n_gpus / args.steps,
                 "peak_source": "yg_fp64_peak: DFMA / RK4-step micro-benchmarks measured live on this GPU (best of "

@@ -230,3 +230,15 @@ def test_pooled_moments_and_rhat_from_sufficient_statistics():
     B_over_n = mean_c.var(axis=0, ddof=1)
     np.testing.assert_allclose(out["rhat"], np.sqrt(((n - 1) / n * W + B_over_n) / W), rtol=1e-12)
     assert abs(out["acceptance_rate"] - 1234.0 / (C * n)) < 1e-15
+
+
+def test_trajectory_file_format_roundtrip(tmp_path):
+    """io.py on the host: [length, d, n_chains] float64 .npy + JSON side-car."""
+    from yagre_mcmc_b200 import io
+    x = np.random.default_rng(0).standard_normal((7, 2, 5))
+    f = io.save_trajectory(str(tmp_path / "t.npy"), x, thin=3, chain_offset=40)
+    y, side = io.load_trajectory(f)
+    assert np.array_equal(x, y) and side["thin"] == 3 and side["layout"] == "[length, d, n_chains]"
+    assert io.as_reference_layout(y).shape == (7, 5, 2)
+    with pytest.raises(ValueError):
+        io.save_trajectory(str(tmp_path / "bad"), np.zeros((3, 3), dtype=np.float32))

@@ -149,6 +149,35 @@ def test_resume_is_bit_exact(case):
     assert end["step_index"] == 20 and end["welford_n"] == ref_state["welford_n"]
 
 
+def test_checkpoint_files_and_trajectory_dump(tmp_path):
+    """io.py: a run resumed from a checkpoint FILE continues bit-exactly; the trajectory dump round-trips."""
+    from yagre_mcmc_b200 import io
+    meta, arrays = bp.lv_problem(True, Nc=16, Nf=64)
+    nc = 200
+    th0 = bp.lv_initial_states(nc)
+    a = _ens(meta, arrays, nc, seed=3, chain_offset=1000)
+    a.set_state(th0)
+    ref = a.run(30, samples=True)["samples"]
+    b = _ens(meta, arrays, nc, seed=3, chain_offset=1000)
+    b.set_state(th0)
+    first = b.run(10, samples=True)["samples"]
+    ck = io.save_checkpoint(str(tmp_path / "ck"), b, extra=dict(note="after 10"))
+    c = _ens(meta, arrays, nc, seed=3, chain_offset=1000)
+    head = io.load_checkpoint(ck, c)
+    assert head["step_index"] == 10 and head["extra"]["note"] == "after 10"
+    second = c.run(20, samples=True)["samples"]
+    assert torch.equal(torch.cat([first, second]), ref)
+    wrong = _ens(meta, arrays, nc, seed=4, chain_offset=1000)
+    with pytest.raises(ValueError, match="seed"):
+        io.load_checkpoint(ck, wrong)
+    f = io.save_trajectory(str(tmp_path / "traj"), ref, thin=1, chain_offset=1000, meta=dict(model="lv"))
+    back, side = io.load_trajectory(f)
+    assert np.array_equal(back, ref.cpu().numpy()) and side["n_chains"] == nc and side["chain_offset"] == 1000
+    assert io.as_reference_layout(back).shape == (30, nc, 2)
+    mm, _ = io.load_trajectory(f, mmap=True)
+    assert np.array_equal(mm[-1], back[-1])
+
+
 def test_thinning_and_outputs():
     meta, arrays = bp.lv_problem(True, Nc=16, Nf=64)
     nc = 200
