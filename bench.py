@@ -245,29 +245,56 @@ def run_gpu_arm(args):
     # ---- end to end through the public API: host theta0 in, host trajectory out ---------------------
     e2e = None
     if not args.no_e2e:
+        # Every step: H2D of the step's initial states (pinned), yg_set_state + yg_run with samples, D2H of the
+        # step's trajectory and accept counts (pinned).  The D2H of step i runs on a copy stream while step i+1
+        # computes (two output buffers); the timed region spans the first H2D to the last D2H.
+        n_e2e = max(5, args.steps // 2)
         host_in = torch.from_numpy(th0).pin_memory()
-        host_out = torch.empty((S, 2, nc), dtype=torch.float64).pin_memory()
-        host_acc = torch.empty((nc,), dtype=torch.int64).pin_memory()
-        e_ms = []
-        for i in range(2 + max(3, args.steps // 4)):
+        host_out = [torch.empty((S, 2, nc), dtype=torch.float64).pin_memory() for _ in range(2)]
+        host_acc = [torch.empty((nc,), dtype=torch.int64).pin_memory() for _ in range(2)]
+        dev_out = [torch.empty((S, 2, nc), dtype=torch.float64, device=dev) for _ in range(2)]
+        dev_acc = [torch.empty((nc,), dtype=torch.int64, device=dev) for _ in range(2)]
+        copied = [None, None]
+        main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+
+        def e2e_step(i):
+            b = i % 2
             flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            if copied[b] is not None:
+                main.wait_event(copied[b])                              # buffer b was read out two steps ago
             ens.set_state(host_in.to(dev, non_blocking=True))           # H2D + log-posterior of the start state
-            out = ens.run(S, samples=True)
-            host_out.copy_(out["samples"], non_blocking=True)           # D2H trajectory
-            host_acc.copy_(ens.state()["n_accept"], non_blocking=True)  # D2H acceptance counts
-            e1.record()
-            torch.cuda.synchronize(dev)
-            if i >= 2:
-                e_ms.append(e0.elapsed_time(e1))
-        et = torch.tensor([float(np.mean(e_ms))], dtype=torch.float64, device=dev)
+            ens.run(S, samples_out=dev_out[b])
+            dev_acc[b].copy_(ens.accept_counts())
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                host_out[b].copy_(dev_out[b], non_blocking=True)        # D2H trajectory
+                host_acc[b].copy_(dev_acc[b], non_blocking=True)        # D2H acceptance counts
+                copied[b] = torch.cuda.Event()
+                copied[b].record(side)
+
+        for i in range(2):
+            e2e_step(i)
+        torch.cuda.synchronize(dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for i in range(n_e2e):
+            e2e_step(i)
+        fin = torch.cuda.Event()
+        fin.record(side)
+        main.wait_event(fin)
+        e1.record(main)
+        torch.cuda.synchronize(dev)
+        et = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(et, op=dist.ReduceOp.MAX)
         e2e = {"value": float(nc) * n_gpus * S / (float(et.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out.numel() * 8 + nc * 8),
-               "ms_per_step": float(et.item()),
-               "path": "ChainEnsemble.set_state(host theta0) + run(S, samples) + trajectory and accept counts to pinned host"}
+               "h2d_bytes_per_step": int(host_in.numel() * 8), "d2h_bytes_per_step": int(host_out[0].numel() * 8 + nc * 8),
+               "ms_per_step": float(et.item()), "steps": n_e2e,
+               "path": "ChainEnsemble.set_state(pinned host theta0) + run(S, samples) + trajectory and accept counts to "
+                       "pinned host; the D2H of a step overlaps the next step's kernels on a copy stream"}
 
     # ---- ESS/s: the sampling run of the example (5,000 steps, burn-in 100), IAT on the device --------
     ess = None

@@ -25,8 +25,10 @@
 //   * epilogue per 16x8 accumulator tile: + b, - data row, * noise precision, squared, summed
 //     per chain; a 4-lane butterfly finishes the row sums, so the four lanes of a chain hold
 //     bit-identical log-posteriors and take the same accept decision without further traffic;
-//   * Philox noise is keyed exactly like the one-chain-per-thread kernels, so results do not
-//     depend on which kernel serves a problem size.
+//   * Philox noise is keyed like the one-chain-per-thread kernels (seed, global chain id, step,
+//     sub-step, pair); the Box-Muller transform of this kernel runs in FP32 (see
+//     philox_normal_pair_f32): d normals per chain-step make the transform, not the GEMM, the
+//     limiter otherwise.
 #include "ensemble.h"
 #include "big_linear.h"
 #include <math_constants.h>
@@ -39,6 +41,26 @@ YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, doubl
         "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
         : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
         : "d"(a0), "d"(a1), "d"(b0));
+}
+
+// Box-Muller on one Philox block with the TRANSFORM in FP32: the two uniforms keep their 53 Philox bits, but
+// log / sqrt / sincospi run on the FP32 pipe (a few dozen FMA-pipe instructions instead of ~150 FP64 ones per
+// pair).  The normals are exact N(0,1) draws up to a relative perturbation of ~1e-7 -- immaterial for a proposal
+// distribution -- and a recorded stream replays bit-exactly.  This kernel draws d normals per chain and step
+// (64 at d = 64) against 2 in the LV kernel, where the FP64 transform stays.
+// Not inlined on purpose: 16 inlined copies (Philox rounds + logf + sincospif) per proposal made the step loop
+// larger than the instruction cache (stall reason no_instruction 2.9 warps per issue in the ncu capture).
+__device__ __noinline__ void philox_normal_pair_f32(uint64_t seed, uint64_t chain, uint64_t step, uint32_t sub, uint32_t b,
+                                                    double &z0, double &z1)
+{
+    const uint4 w = philox_block(seed, chain, step, sub, b);
+    const float u1 = (float)(u53(w.x, w.y) + 0x1.0p-53);   // (0,1]
+    const float u2 = (float)u53(w.z, w.w);
+    const float R = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z0 = (double)(R * cs);
+    z1 = (double)(R * sn);
 }
 
 YG_DEVFN double quad_sum(double v)
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
                     // no branch on k < d: straight-line code lets the scheduler interleave the KQ
                     // independent Philox / Box-Muller chains (padding columns are zeroed below)
                     double z0, z1;
-                    philox_normal_pair(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
+                    philox_normal_pair_f32(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
                     const double recv = __shfl_xor_sync(0xffffffffu, odd ? z0 : z1, 1);
                     zr[0] = odd ? recv : z0;
                     zr[1] = odd ? z1 : recv;

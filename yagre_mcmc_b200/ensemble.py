@@ -155,11 +155,14 @@ class ChainEnsemble:
             check(self.lib.yg_set_state(self._h, C.c_void_p(soa.data_ptr()), self._stream()))
         return self
 
-    def run(self, n_steps, thin=1, samples=True, accepted=False, logpost=False, inject=None, record=False):
+    def run(self, n_steps, thin=1, samples=True, accepted=False, logpost=False, inject=None, record=False,
+            samples_out=None):
         """Runs n_steps transitions of every chain.
 
         inject: dict(z=[n_steps,J,d,n], u_c=[n_steps,J,n], u_f=[n_steps,n]) device or host arrays.
         record: Philox noise, and the noise actually used is returned in the same layout.
+        samples_out: optional preallocated device tensor [n_steps/thin, d, n] to write the samples into
+                (no allocation in the call; the caller owns its lifetime across streams).
         Returns a dict of device tensors: samples [n_steps/thin, d, n], accepted [n_steps, n] uint8,
         logpost [n_steps/thin, levels, n].
         """
@@ -168,7 +171,13 @@ class ChainEnsemble:
         out = YgOutputs()
         res = {}
         n_out = n_steps // thin
-        if samples:
+        if samples_out is not None:
+            if (tuple(samples_out.shape) != (n_out, d, n) or samples_out.dtype != torch.float64
+                    or not samples_out.is_contiguous() or samples_out.device != self.device):
+                raise ValueError(f"samples_out must be a contiguous float64 device tensor of shape {(n_out, d, n)}")
+            res['samples'] = samples_out
+            out.samples_dev = samples_out.data_ptr()
+        elif samples:
             res['samples'] = self._empty(n_out, d, n)
             out.samples_dev = res['samples'].data_ptr()
         if accepted:
@@ -230,6 +239,15 @@ class ChainEnsemble:
         c = self.counters()
         r['step_index'], r['welford_n'] = c['step_index'], c['welford_n']
         return r
+
+    def accept_counts(self):
+        """Per-chain accepted transitions since set_state: device tensor [n_chains] int64 (asynchronous)."""
+        st = YgState()
+        out = self._empty(self.n_chains, dtype=torch.int64)
+        st.n_accept_dev = out.data_ptr()
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_get_state(self._h, C.byref(st), self._stream()))
+        return out
 
     def load_state(self, r):
         st = YgState()
