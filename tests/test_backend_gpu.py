@@ -567,3 +567,61 @@ def test_c2_gaussian_target_moments():
     flat = s.transpose(0, 2, 1).reshape(-1, 2)
     np.testing.assert_allclose(flat.mean(0), bp.GAUSS2D_MEAN, atol=0.02)
     np.testing.assert_allclose(np.cov(flat.T), bp.GAUSS2D_COV, atol=0.05)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases: smallest / largest / ragged sizes
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", ["one_chain", "one_design_point", "one_rk4_step", "j1", "many_design_points"])
+def test_lv_edge_shapes_against_oracle(shape):
+    kw = dict(one_chain=dict(), one_design_point=dict(n_data=1), one_rk4_step=dict(Nc=1, Nf=3),
+              j1=dict(J=1), many_design_points=dict(n_data=37, Nc=8, Nf=24))[shape]
+    nc = 1 if shape == "one_chain" else 97
+    meta, arrays = bp.lv_problem(True, **({"Nc": 16, "Nf": 48} | kw))
+    th0 = bp.lv_initial_states(nc)
+    ens = _ens(meta, arrays, nc, seed=3)
+    ens.set_state(th0)
+    out = ens.run(15, samples=True, accepted=True, logpost=True, record=True)
+    ref = _replay(meta, arrays, th0, out)
+    assert int((out["accepted"].cpu().numpy().T != ref["accepted"]).sum()) == 0
+    assert rel_err(out["samples"].cpu().numpy().transpose(2, 0, 1), ref["traj"][:, 1:]).max() <= 1e-12
+    lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, 1], ref["logpost_L1"][:, 1:]).max() <= LOGPOST_RTOL
+
+
+def test_zero_steps_and_repeated_short_runs():
+    """n_steps = 0 is a no-op; 12 runs of 1 transition equal one run of 12 (step index carries over)."""
+    meta, arrays = bp.lv_problem(True, Nc=16, Nf=48)
+    nc = 130
+    th0 = bp.lv_initial_states(nc)
+    a = _ens(meta, arrays, nc, seed=9)
+    a.set_state(th0)
+    ref = a.run(12, samples=True)["samples"]
+    b = _ens(meta, arrays, nc, seed=9)
+    b.set_state(th0)
+    assert b.run(0, samples=True)["samples"].shape[0] == 0
+    parts = [b.run(1, samples=True)["samples"] for _ in range(12)]
+    assert torch.equal(torch.cat(parts), ref)
+    assert b.counters()["step_index"] == 12
+
+
+def test_c5_full_ensemble_on_one_gpu():
+    """524,288 chains (the whole C5 ensemble) on one device: every chain advances, no chain is lost at the
+    CTA chunk boundaries (each CTA walks its 3,543 chains in chunks of <= 1,024)."""
+    nc = 524288
+    meta, arrays = bp.lv_problem(True)
+    ens = _ens(meta, arrays, nc, seed=21)
+    th0 = bp.lv_initial_states(nc)
+    ens.set_state(th0)
+    out = ens.run(4, samples=True, accepted=True)
+    c = ens.counters()
+    assert c["transitions"] == 4 * nc and c["coarse_evals"] >= 3 * 4 * nc - 8
+    acc = out["accepted"]
+    assert torch.equal(ens.state()["n_accept"], acc.sum(dim=0).to(torch.int64))
+    moved = (out["samples"][0] != torch.as_tensor(th0.T, device="cuda")).any(dim=0)
+    assert torch.equal(moved, acc[0].bool())
+    # chain-offset keying: chains [1000, 1100) of the big run equal a 100-chain handle with chain_offset 1000
+    sub = _ens(meta, arrays, 100, seed=21, chain_offset=1000)
+    sub.set_state(th0[1000:1100])
+    assert torch.equal(sub.run(4, samples=True)["samples"], out["samples"][:, :, 1000:1100])

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     off += sizeof(int) * (size_t)nd_max * cmax;
     unsigned char *evald = smem_raw + off;                                 // [cmax]
     off += (cmax + 15) & ~15;
+    off = (off + 15) & ~size_t(15);      // the int arrays above leave 4-byte alignment when n_data * cmax is odd
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + off);
     int *nact = reinterpret_cast<int *>(mbar + 1);                         // [2]
     unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [4]
@@ -499,6 +500,7 @@ size_t lv_smem_bytes(const yg_ensemble *e, int cmax, int nd_max)
     off += sizeof(int) * 2 * cmax;
     off += sizeof(int) * (size_t)nd_max * cmax;           // segdone
     off += (cmax + 15) & ~15;
+    off = (off + 15) & ~size_t(15);
     off += 8 + 8 + 32 + 8;
     return (off + 15) & ~size_t(15);
 }
