@@ -211,7 +211,8 @@ int yg_logpost(yg_ensemble *e, int32_t level, const double *theta_dev, int64_t n
 
 /* samples_dev[n_samples, d, n_chains] -> iat_dev[n_chains] (max over coordinates, Sokal window c),
  * ess_dev[n_chains] = n_samples / max(iat,1) (integer division), either may be NULL.
- * method: 0 = 'mean', 1 = 'max'. */
+ * method: 0 = 'mean', 1 = 'max'.  Series of more than 25,600 samples use a stream-ordered scratch
+ * allocation (cudaMallocAsync / cudaFreeAsync on `stream`; still no host synchronisation). */
 int yg_iat_ess(const double *samples_dev, int64_t n_samples, int32_t d, int64_t n_chains,
                int32_t method, double sokal_const, int64_t *iat_dev, int64_t *ess_dev, void *stream);
 

@@ -242,3 +242,20 @@ def test_trajectory_file_format_roundtrip(tmp_path):
     assert io.as_reference_layout(y).shape == (7, 5, 2)
     with pytest.raises(ValueError):
         io.save_trajectory(str(tmp_path / "bad"), np.zeros((3, 3), dtype=np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under yagre_mcmc_b200/ may import, load or execute it
+    (no CPU fallback), and the package must not read /root/reference."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "yagre_mcmc_b200")
+    bad = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|libyagre_oracle|/root/reference|yagremcmc\b(?!/)", txt, re.M) and f.endswith(".py"):
+                    if re.search(r"^\s*(from|import)\s+(oracle|yagremcmc)\b|libyagre_oracle", txt, re.M):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -388,6 +388,26 @@ def test_iat_kernel_many_chains_matches_oracle():
     assert np.array_equal(ess.cpu().numpy(), N // np.maximum(want, 1))
 
 
+def test_iat_kernel_long_series():
+    """Series longer than the shared-memory capacity (C2 / C3 run 100,000 / 50,000 steps per chain) go through
+    the stream-ordered scratch path: same numbers as the oracle's restatement of the reference."""
+    from oracle import cport
+    from yagre_mcmc_b200.ensemble import iat_ess
+    rng = np.random.default_rng(4)
+    N, d, nc = 30000, 2, 5
+    rho = np.array([[0.0, 0.5, 0.9, 0.97, 0.99], [0.3, 0.2, 0.95, 0.5, 0.9]])
+    e = rng.standard_normal((N, d, nc))
+    x = np.zeros((N, d, nc))
+    for t in range(1, N):
+        x[t] = rho * x[t - 1] + e[t]
+    for method in ("max", "mean"):
+        iat, ess = iat_ess(torch.as_tensor(x, device="cuda"), method)
+        want = np.array([cport.iat(x[:, :, c], method) for c in range(nc)])
+        assert np.array_equal(iat.cpu().numpy(), want), (method, iat, want)
+        assert np.array_equal(ess.cpu().numpy(), N // np.maximum(want, 1))
+    assert want.max() > 20
+
+
 def test_split_moments_and_pooled_stats_match_numpy():
     from yagre_mcmc_b200.ensemble import split_moments
     from yagre_mcmc_b200.parallel import moments_from_stats, split_rhat

@@ -40,15 +40,17 @@ __device__ void block_sum4(double (&v)[IAT_LAGS], double *red /* [4][IAT_LAGS] *
     }
 }
 
-// One CTA per chain.  The series is staged in shared memory; lags are produced four at a
-// time until Sokal's criterion M >= c * tau(M) is met (autocorrelation.py:53-59: argmin of
-// the boolean "M < c*tau[M]" = first False; all True -> index 0).
+// One CTA per chain.  The series is staged contiguously -- in shared memory, or for series longer
+// than 25,600 samples (C2 / C3 run 100,000 / 50,000 steps) in a per-CTA slice of a global scratch
+// buffer that stays L2 resident; lags are produced four at a time until Sokal's criterion
+// M >= c * tau(M) is met (autocorrelation.py:53-59: argmin of the boolean "M < c*tau[M]" = first
+// False; all True -> index 0).
 __global__ void __launch_bounds__(IAT_THREADS) iat_kernel(const double *samples, int64_t ns, int d, int64_t nc,
                                                           int method, double sokal, int64_t *iat_out,
-                                                          int64_t *ess_out)
+                                                          int64_t *ess_out, double *scratch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *x = reinterpret_cast<double *>(smem_raw);          // [ns]
+    double *x = scratch ? scratch + (size_t)blockIdx.x * (size_t)ns : reinterpret_cast<double *>(smem_raw);   // [ns]
     __shared__ double red[(IAT_THREADS / 32) * IAT_LAGS];
     const int tid = threadIdx.x;
     for (int64_t chain = blockIdx.x; chain < nc; chain += gridDim.x) {
@@ -233,21 +235,23 @@ extern "C" int yg_iat_ess(const double *samples_dev, int64_t n_samples, int32_t 
         yg_set_error("yg_iat_ess: invalid arguments");
         return YG_ERR_INVALID;
     }
-    const size_t smem = sizeof(double) * (size_t)n_samples;
-    if (smem > 200 * 1024) {
-        yg_set_error("yg_iat_ess: series of %lld samples does not fit shared memory (max 25600)",
-                     (long long)n_samples);
-        return YG_ERR_UNSUPPORTED;
-    }
-    YG_CUDA_CHECK(cudaFuncSetAttribute(iat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = sizeof(double) * (size_t)n_samples;
+    const bool long_series = smem > 200 * 1024;
+    if (long_series) smem = 0;
+    else YG_CUDA_CHECK(cudaFuncSetAttribute(iat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const int per_sm = long_series ? 2 : (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
     const int grid = (int)std::min<int64_t>(n_chains, (int64_t)sms * per_sm);
-    iat_kernel<<<grid, IAT_THREADS, smem, (cudaStream_t)stream>>>(samples_dev, n_samples, d, n_chains, method,
-                                                                   sokal_const, (int64_t *)iat_dev, (int64_t *)ess_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scratch = nullptr;
+    if (long_series)     // stream-ordered scratch (one contiguous copy of the series per CTA): no host synchronisation
+        YG_CUDA_CHECK(cudaMallocAsync((void **)&scratch, sizeof(double) * (size_t)grid * (size_t)n_samples, st));
+    iat_kernel<<<grid, IAT_THREADS, smem, st>>>(samples_dev, n_samples, d, n_chains, method, sokal_const,
+                                                (int64_t *)iat_dev, (int64_t *)ess_dev, scratch);
     YG_CUDA_CHECK(cudaGetLastError());
+    if (long_series) YG_CUDA_CHECK(cudaFreeAsync(scratch, st));
     return YG_OK;
 }
 
