@@ -141,7 +141,7 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     }
     tail_len += kp;
     tail_len = (tail_len + 1) & ~size_t(1);
-    if (sizeof(double) * (tail_len + (size_t)8 * 16 * ks) > 226 * 1024) {      // blob + per-warp state tiles
+    if (sizeof(double) * (tail_len + (size_t)16 * 8 * ks) > 226 * 1024) {      // blob + per-warp state tiles (16 warps x 8 chains)
         yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
         return YG_ERR_UNSUPPORTED;
     }

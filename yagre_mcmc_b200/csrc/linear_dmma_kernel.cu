@@ -14,15 +14,17 @@
 //   Welford diagnostics  chain/diagnostics.py:91-94, statistics/estimation.py:36-53 (diagonal M2)
 //
 // B200 mapping
-//   * persistent CTAs (one per SM), 8 warps; a warp owns a tile of 16 chains (the M extent of
-//     m16n8k4) for ALL n_steps.  Proposals live in registers in A-fragment layout: lane
-//     (g = lane / 4, t = lane % 4) holds p[row g and g+8][k = 4 i + t], so a proposal is already
+//   * persistent CTAs (one per SM), 16 warps; a warp owns a tile of 8 chains (the M extent of
+//     m8n8k4 = the native DMMA.8x8x4) for ALL n_steps: 8-row tiles halve the registers per thread
+//     (d = 64: 32 per operand copy), so 16 warps are resident and the non-GEMM work of a warp
+//     (noise, accept, Welford) overlaps the GEMMs of three others on its sub-partition.  Proposals live in registers in A-fragment layout: lane
+//     (g = lane / 4, t = lane % 4) holds p[row g][k = 4 i + t], so a proposal is already
 //     the A operand of the GEMM; the current state of the tile sits in a per-warp shared-memory
 //     tile in the same lane-private pattern (d = 64 needs 64 registers per operand copy);
 //   * G of every level is staged once per CTA into shared memory (row stride = 4 mod 16 doubles:
-//     the B-fragment loads of a warp are bank-conflict free) and shared by the 8 warps; with 16
-//     chains per B fragment the shared-memory traffic is 1/2 of the DMMA issue time;
-//   * epilogue per 16x8 accumulator tile: + b, - data row, * noise precision, squared, summed
+//     the B-fragment loads of a warp are bank-conflict free) and shared by the 16 warps: one 8-byte
+//     load per lane and DMMA, half of the shared-memory bandwidth at full DMMA rate;
+//   * epilogue per 8x8 accumulator tile: + b, - data row, * noise precision, squared, summed
 //     per chain; a 4-lane butterfly finishes the row sums, so the four lanes of a chain hold
 //     bit-identical log-posteriors and take the same accept decision without further traffic;
 //   * Philox noise is keyed like the one-chain-per-thread kernels (seed, global chain id, step,
@@ -34,6 +36,13 @@
 #include <math_constants.h>
 
 namespace {
+
+YG_DEVFN void dmma_m8n8k4(double &c0, double &c1, double a0, double b0)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a0), "d"(b0));
+}
 
 YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double b0)
 {
@@ -48,7 +57,7 @@ YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, doubl
 // pair).  The normals are exact N(0,1) draws up to a relative perturbation of ~1e-7 -- immaterial for a proposal
 // distribution -- and a recorded stream replays bit-exactly.  This kernel draws d normals per chain and step
 // (64 at d = 64) against 2 in the LV kernel, where the FP64 transform stays.
-// Not inlined on purpose: 16 inlined copies (Philox rounds + logf + sincospif) per proposal made the step loop
+// Not inlined on purpose: inlined copies (Philox rounds + logf + sincospif) per proposal made the step loop
 // larger than the instruction cache (stall reason no_instruction 2.9 warps per issue in the ncu capture).
 __device__ __noinline__ void philox_normal_pair_f32(uint64_t seed, uint64_t chain, uint64_t step, uint32_t sub, uint32_t b,
                                                     double &z0, double &z1)
@@ -80,60 +89,59 @@ struct SmemLevel {
     int np;
 };
 
-// log-posterior of the two chains (rows g, g+8) whose parameters are spread over the quad:
-// a[r][i] = theta_row_r[4 i + t].  Every lane of a quad returns the same two values.
+// log-posterior of the chain (row g of the warp's 8 x d tile) whose parameters are spread over the quad:
+// a[i] = theta[4 i + t].  Every lane of a quad returns the same value.
 template <int KQ>
-YG_DEVFN void logpost_tile(const SmemLevel &L, const int ks, const double (&a)[2][KQ], const int g, const int t,
-                           double &lp_r0, double &lp_r1)
+YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)[KQ], const int g, const int t)
 {
     // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + q_const  (exact identity;
     // no cancellation: the row scatter is a precomputed constant)
-    double q0 = 0.0, q1 = 0.0;
-    auto epilogue = [&](const int nb, const double c0, const double c1, const double c2, const double c3) {
+    double q = 0.0;
+    auto epilogue = [&](const int nb, const double c0, const double c1) {
         const int col = nb + 2 * t;
-        const double b0 = L.bd[col], b1 = L.bd[col + 1], w0 = L.nw[col], w1 = L.nw[col + 1];
-        const double e00 = c0 + b0, e01 = c1 + b1, e10 = c2 + b0, e11 = c3 + b1;     // A @ theta + b - mean(data)
-        q0 = fma(w1 * e01, e01, fma(w0 * e00, e00, q0));
-        q1 = fma(w1 * e11, e11, fma(w0 * e10, e10, q1));
+        const double e0 = c0 + L.bd[col], e1 = c1 + L.bd[col + 1];      // A @ theta + b - mean(data)
+        q = fma(L.nw[col + 1] * e1, e1, fma(L.nw[col] * e0, e0, q));
     };
-    // two independent accumulator tiles per pass: a chain of dependent DMMAs alone cannot fill the pipe
+    // four independent accumulator tiles per pass: a chain of dependent DMMAs alone cannot fill the pipe
     int nb = 0;
-    for (; nb + 16 <= L.np; nb += 16) {
-        double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
-        const double *Gb0 = L.G + (size_t)(nb + g) * ks + t, *Gb1 = Gb0 + (size_t)8 * ks;
-#pragma unroll
-        for (int i = 0; i < KQ; i++) {
-            dmma_m16n8k4(c[0][0], c[0][1], c[0][2], c[0][3], a[0][i], a[1][i], Gb0[4 * i]);
-            dmma_m16n8k4(c[1][0], c[1][1], c[1][2], c[1][3], a[0][i], a[1][i], Gb1[4 * i]);
-        }
-        epilogue(nb, c[0][0], c[0][1], c[0][2], c[0][3]);
-        epilogue(nb + 8, c[1][0], c[1][1], c[1][2], c[1][3]);
-    }
-    for (; nb < L.np; nb += 8) {
-        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    for (; nb + 32 <= L.np; nb += 32) {
+        double c[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
 #pragma unroll
-        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, a[0][i], a[1][i], Gb[4 * i]);
-        epilogue(nb, c0, c1, c2, c3);
+        for (int i = 0; i < KQ; i++) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) dmma_m8n8k4(c[m][0], c[m][1], a[i], Gb[(size_t)(8 * m) * ks + 4 * i]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) epilogue(nb + 8 * m, c[m][0], c[m][1]);
     }
-    const double s0 = quad_sum(q0) + L.q_const, s1 = quad_sum(q1) + L.q_const;
-    double p0 = 0.0, p1 = 0.0;
+    for (; nb < L.np; nb += 8) {
+        double c0 = 0.0, c1 = 0.0;
+        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) dmma_m8n8k4(c0, c1, a[i], Gb[4 * i]);
+        epilogue(nb, c0, c1);
+    }
+    double pr = 0.0;
 #pragma unroll
     for (int i = 0; i < KQ; i++) {
-        const double m = L.pmean[4 * i + t], w = L.pprec[4 * i + t];
-        const double x0 = a[0][i] - m, x1 = a[1][i] - m;
-        p0 = fma(w * x0, x0, p0);
-        p1 = fma(w * x1, x1, p1);
+        const double x = a[i] - L.pmean[4 * i + t];
+        pr = fma(L.pprec[4 * i + t] * x, x, pr);
     }
-    lp_r0 = -0.5 * s0 + (-0.5 * quad_sum(p0));
-    lp_r1 = -0.5 * s1 + (-0.5 * quad_sum(p1));
+    return -0.5 * (quad_sum(q) + L.q_const) + (-0.5 * quad_sum(pr));
 }
 
-template <int KQ, bool TWO_LEVEL>
-__global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh)
+constexpr int BIG_WARPS = 16;      // warps per CTA: 8 chains each, <= 128 registers per thread
+
+// FREE_NOISE = true: the production instance (Philox noise only).  The injected / recorded noise paths of the
+// parity tests live in the FREE_NOISE = false instance, which keeps the step loop of the production one small
+// enough for the instruction cache (stall reason no_instruction in profiles/r01_linear_dmma.md).
+template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
+__global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh)
 {
+    const int noise_mode = FREE_NOISE ? (int)YG_NOISE_PHILOX : a.noise_mode;
     extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3, odd = t & 1;
     // ---- stage the problem into shared memory -------------------------------------------------
     const DevBigHeader H = *gh;
     const double *gtail = reinterpret_cast<const double *>(gh + 1);
@@ -151,274 +159,223 @@ __global__ void __launch_bounds__(256, 1) linear_dmma_mh_kernel(const RunArgs a,
         Lv[l].np = H.lvl[l].np;
     }
     const double *propL = smem + H.propL_off;      // [kp] diagonal proposal factor (zero beyond dim)
-    // current state of the warp's 16 chains: [16][ks] doubles after the problem blob; lane (g, t) only
-    // ever touches its own slots (rows g, g+8, columns 4 i + t), so no synchronisation is needed, and
-    // the row stride (4 mod 16 doubles) makes the accesses bank-conflict free
-    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * 16 * H.ks;
-#define TH(r, i) ths[((r) * 8 + g) * ks + 4 * (i) + t]
+    // current state of the warp's 8 chains: [8][ks] doubles after the problem blob; lane (g, t) only ever
+    // touches its own slots (row g, columns 4 i + t), so no synchronisation is needed, and the row stride
+    // (4 mod 16 doubles) makes the accesses bank-conflict free
     const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * 8 * ks;
+#define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
 
-    const int64_t n_tiles = (N + 15) / 16;
-    for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
-        // rows of this lane: chains gr[0], gr[1] (a row beyond n_chains is computed but never stored)
-        int64_t gr[2] = {tile * 16 + g, tile * 16 + g + 8};
-        bool live[2] = {gr[0] < N, gr[1] < N};
-        double lp0[2], lp1[2];
-        unsigned long long nacc[2];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int64_t gg = live[r] ? gr[r] : 0;
-#pragma unroll
-            for (int i = 0; i < KQ; i++) {
-                const int k = 4 * i + t;
-                const bool in = k < d;
-                TH(r, i) = in ? a.theta[(int64_t)k * N + gg] : 0.0;
-            }
-            lp0[r] = a.logpost[gg];
-            lp1[r] = TWO_LEVEL ? a.logpost[N + gg] : 0.0;
-            nacc[r] = a.n_accept[gg];
+    const int64_t n_tiles = (N + 7) / 8;
+    for (int64_t tile = (int64_t)blockIdx.x * BIG_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * BIG_WARPS) {
+        // this lane's chain (a row beyond n_chains is computed but never stored)
+        const int64_t gr = tile * 8 + g;
+        const bool live = gr < N;
+        const int64_t gg = live ? gr : 0;
+        const uint64_t gid = (uint64_t)(a.chain_offset + gg);
+#pragma unroll 1
+        for (int i = 0; i < KQ; i++) {
+            const int k = 4 * i + t;
+            TH(i) = (k < d) ? a.theta[(int64_t)k * N + gg] : 0.0;
         }
+        double lp0 = a.logpost[gg], lp1 = TWO_LEVEL ? a.logpost[N + gg] : 0.0;
+        unsigned long long nacc = a.n_accept[gg];
 
         // Welford (estimation.py:36-53, diagonal M2) in run-length form: a chain that stays at x for m
         // consecutive steps contributes  n' = n + m, mean' = mean + (x - mean) m / n',
         // M2' = M2 + (x - mean)^2 n m / n'  -- algebraically the m sequential updates.  With the
         // accumulators in (L2-resident) global memory this touches them once per accepted move
-        // instead of once per step; the registers stay with the GEMM operands.
-        double run[2] = {0.0, 0.0}, wn[2] = {(double)a.welford_n0, (double)a.welford_n0};
-        // flush[r]: row r leaves its state now.  Both rows go through ONE pass with the loads of a
-        // batch of columns issued before any store (a store may alias the next load for the compiler).
-        auto welford_flush = [&](const bool f0, const bool f1) {
-            const bool fl[2] = {f0 && live[0] && run[0] != 0.0, f1 && live[1] && run[1] != 0.0};
-            if (!__any_sync(0xffffffffu, fl[0] || fl[1])) return;
-            double c1[2], c2[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const double n1 = wn[r] + run[r];
-                c1[r] = run[r] / n1;
-                c2[r] = wn[r] * c1[r];
-            }
-            constexpr int B = KQ < 4 ? KQ : 4;
-#pragma unroll
+        // instead of once per step; the registers stay with the GEMM operands.  Loads of a batch of
+        // columns are issued before any store (a store may alias the next load for the compiler).
+        double run = 0.0, wn = (double)a.welford_n0;
+        auto welford_flush = [&](const bool f) {
+            const bool fl = f && live && run != 0.0;
+            if (!__any_sync(0xffffffffu, fl)) return;
+            const double n1 = wn + run, c1 = run / n1, c2 = wn * c1;
+            constexpr int B = KQ < 8 ? KQ : 8;
+#pragma unroll 1
             for (int i0 = 0; i0 < KQ; i0 += B) {
-                double m0[2][B], v0[2][B];
+                double m0[B], v0[B];
 #pragma unroll
-                for (int r = 0; r < 2; r++)
+                for (int i = 0; i < B; i++) {
+                    const int k = 4 * (i0 + i) + t;
+                    const bool on = fl && k < d;
+                    m0[i] = on ? a.w_mean[(int64_t)k * N + gr] : 0.0;
+                    v0[i] = on ? a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] : 0.0;
+                }
 #pragma unroll
-                    for (int i = 0; i < B; i++) {
-                        const int k = 4 * (i0 + i) + t;
-                        const bool on = fl[r] && k < d;
-                        m0[r][i] = on ? a.w_mean[(int64_t)k * N + gr[r]] : 0.0;
-                        v0[r][i] = on ? a.w_m2[(int64_t)big_w2_index(k, d) * N + gr[r]] : 0.0;
+                for (int i = 0; i < B; i++) {
+                    const int k = 4 * (i0 + i) + t;
+                    if (fl && k < d) {
+                        const double dl = TH(i0 + i) - m0[i];
+                        a.w_mean[(int64_t)k * N + gr] = fma(dl, c1, m0[i]);
+                        a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] = fma(dl * dl, c2, v0[i]);
                     }
-#pragma unroll
-                for (int r = 0; r < 2; r++)
-#pragma unroll
-                    for (int i = 0; i < B; i++) {
-                        const int k = 4 * (i0 + i) + t;
-                        if (fl[r] && k < d) {
-                            const double dl = TH(r, i0 + i) - m0[r][i];
-                            a.w_mean[(int64_t)k * N + gr[r]] = fma(dl, c1[r], m0[r][i]);
-                            a.w_m2[(int64_t)big_w2_index(k, d) * N + gr[r]] = fma(dl * dl, c2[r], v0[r][i]);
-                        }
-                    }
+                }
             }
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-                if (fl[r]) { wn[r] += run[r]; run[r] = 0.0; }
+            if (fl) { wn += run; run = 0.0; }
         };
 
-        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels:
-        // pair b of sub-step j gives z[2b], z[2b+1].  The even lane of a lane pair draws the pair for
-        // row g, the odd lane for row g+8, and they swap the halves they do not own: one Philox block
-        // and one Box-Muller per lane and 4 parameters.
-        auto propose = [&](auto &&src, int64_t n, int j, double (&p)[2][KQ], bool (&eq)[2]) {
-            const int odd = t & 1;
-            const int64_t g_mine = odd ? (live[1] ? gr[1] : 0) : (live[0] ? gr[0] : 0);
-            const uint64_t gid = (uint64_t)(a.chain_offset + g_mine);
-            bool same[2] = {true, true};
+        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels: pair b of
+        // sub-step j gives z[2b], z[2b+1].  Columns 4i+t and 4i+(t^1) of a lane pair are the two halves of
+        // pair b = (4i + (t & ~1)) / 2: the even lane draws the pairs of even i, the odd lane those of odd
+        // i, and they swap the halves they do not own -- one Philox block + one Box-Muller per lane and
+        // 4 parameters.
+        auto propose = [&](auto &&src, int64_t n, int j, double (&p)[KQ]) {
+            bool same = true;
 #pragma unroll
-            for (int i = 0; i < KQ; i++) {
-                const int k = 4 * i + t;
-                double zr[2] = {0.0, 0.0};
-                if (a.noise_mode == YG_NOISE_INJECT) {
-                    if (k < d) {
+            for (int i2 = 0; i2 < KQ; i2 += 2) {
+                double zv[2] = {0.0, 0.0};                 // z of columns 4 i2 + t and 4 (i2 + 1) + t
+                if (noise_mode == YG_NOISE_INJECT) {
 #pragma unroll
-                        for (int r = 0; r < 2; r++) zr[r] = a.z[((n * J + j) * d + k) * N + (live[r] ? gr[r] : 0)];
+                    for (int e = 0; e < 2; e++) {
+                        const int k = 4 * (i2 + e) + t;
+                        if (k < d && i2 + e < KQ) zv[e] = a.z[((n * J + j) * d + k) * N + gg];
                     }
                 } else {
-                    // no branch on k < d: straight-line code lets the scheduler interleave the KQ
-                    // independent Philox / Box-Muller chains (padding columns are zeroed below)
+                    const int i_mine = i2 + odd;           // the i whose pair this lane draws
                     double z0, z1;
-                    philox_normal_pair_f32(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)(k >> 1), z0, z1);
+                    philox_normal_pair_f32(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j,
+                                           (uint32_t)((4 * i_mine + (t & ~1)) >> 1), z0, z1);
+                    // even lane keeps z0 of its pair (column 4 i2 + t), needs z0 of the odd lane's pair (i2 + 1);
+                    // odd lane keeps z1 of its pair (column 4 (i2+1) + t), needs z1 of the even lane's pair (i2)
                     const double recv = __shfl_xor_sync(0xffffffffu, odd ? z0 : z1, 1);
-                    zr[0] = odd ? recv : z0;
-                    zr[1] = odd ? z1 : recv;
-                    if (k >= d) zr[0] = zr[1] = 0.0;
-                    if (a.noise_mode == YG_NOISE_RECORD && k < d) {
+                    zv[0] = odd ? recv : z0;
+                    zv[1] = odd ? z1 : recv;
 #pragma unroll
-                        for (int r = 0; r < 2; r++)
-                            if (live[r]) a.z[((n * J + j) * d + k) * N + gr[r]] = zr[r];
+                    for (int e = 0; e < 2; e++) {
+                        const int k = 4 * (i2 + e) + t;
+                        if (k >= d || i2 + e >= KQ) zv[e] = 0.0;
+                        else if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[e];
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const double sv = src(r, i);
-                    p[r][i] = __dadd_rn(sv, __dmul_rn(propL[k], zr[r]));
-                    same[r] = same[r] && (p[r][i] == sv);
+                for (int e = 0; e < 2; e++) {
+                    if (i2 + e < KQ) {
+                        const double sv = src(i2 + e);
+                        p[i2 + e] = __dadd_rn(sv, __dmul_rn(propL[4 * (i2 + e) + t], zv[e]));
+                        same = same && (p[i2 + e] == sv);
+                    }
                 }
             }
             // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const unsigned m = __ballot_sync(0xffffffffu, same[r]);
-                eq[r] = ((m >> (4 * g)) & 0xFu) == 0xFu;
-            }
+            const unsigned m = __ballot_sync(0xffffffffu, same);
+            return ((m >> (4 * g)) & 0xFu) == 0xFu;
         };
 
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
             // FullDiagnostics: Welford of the pre-transition state (diagnostics.py:91-94): the state of
             // this step is seen once more; the accumulators are touched when the state changes.
-            run[0] += 1.0; run[1] += 1.0;
-            bool accepted[2] = {false, false};
+            run += 1.0;
+            bool accepted = false;
             if (!TWO_LEVEL) {
-                double p[2][KQ];
-                bool eq[2];
-                propose([&](int r, int i) { return TH(r, i); }, n, 0, p, eq);
-                double lpp[2];
-                logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const int64_t gg = live[r] ? gr[r] : 0;
-                    if (!eq[r]) {                                           // metropolisHastings.py:60-61
-                        if (t == 0 && live[r]) cnt_ev0++;
-                        double u;
-                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
-                        else {
-                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, YG_SUB_FINE);
-                            if (a.noise_mode == YG_NOISE_RECORD && live[r] && t == 0) a.u_f[n * N + gg] = u;
-                        }
-                        accepted[r] = accept_rule(lpp[r] - lp0[r], u);
+                double p[KQ];
+                const bool eq = propose([&](int i) { return TH(i); }, n, 0, p);
+                const double lpp = logpost_tile<KQ>(Lv[0], ks, p, g, t);
+                if (!eq) {                                              // metropolisHastings.py:60-61
+                    if (t == 0 && live) cnt_ev0++;
+                    double u;
+                    if (noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
+                    else {
+                        u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                        if (noise_mode == YG_NOISE_RECORD && live && t == 0) a.u_f[n * N + gg] = u;
                     }
+                    accepted = accept_rule(lpp - lp0, u);
                 }
-                welford_flush(accepted[0], accepted[1]);
+                welford_flush(accepted);
+                if (accepted) {
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    if (accepted[r]) {
-#pragma unroll
-                        for (int i = 0; i < KQ; i++) TH(r, i) = p[r][i];
-                        lp0[r] = lpp[r];
-                    }
+                    for (int i = 0; i < KQ; i++) TH(i) = p[i];
+                    lp0 = lpp;
                 }
             } else {
-                double s[2][KQ], p[2][KQ], lps[2] = {lp0[0], lp0[1]};
+                double s[KQ], p[KQ], lps = lp0;
 #pragma unroll
-                for (int r = 0; r < 2; r++)
+                for (int i = 0; i < KQ; i++) s[i] = TH(i);
+                for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
+                    const bool eq = propose([&](int i) { return s[i]; }, n, j, p);
+                    const double lpp = logpost_tile<KQ>(Lv[0], ks, p, g, t);
+                    if (eq) continue;
+                    if (t == 0 && live) cnt_ev0++;
+                    const int64_t ui = (n * J + j) * N + gg;
+                    double u;
+                    if (noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
+                    else {
+                        u = philox_uniform(a.seed, gid, step, (uint32_t)j);
+                        if (noise_mode == YG_NOISE_RECORD && live && t == 0) a.u_c[ui] = u;
+                    }
+                    if (accept_rule(lpp - lps, u)) {
 #pragma unroll
-                    for (int i = 0; i < KQ; i++) s[r][i] = TH(r, i);
-                for (int j = 0; j < J; j++) {                               // coarse sub-chain, mlda.py:100-110
-                    bool eq[2];
-                    propose([&](int r, int i) { return s[r][i]; }, n, j, p, eq);
-                    double lpp[2];
-                    logpost_tile<KQ>(Lv[0], ks, p, g, t, lpp[0], lpp[1]);
-#pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int64_t gg = live[r] ? gr[r] : 0;
-                        if (eq[r]) continue;
-                        if (t == 0 && live[r]) cnt_ev0++;
-                        const int64_t ui = (n * J + j) * N + gg;
-                        double u;
-                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
-                        else {
-                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, (uint32_t)j);
-                            if (a.noise_mode == YG_NOISE_RECORD && live[r] && t == 0) a.u_c[ui] = u;
-                        }
-                        if (accept_rule(lpp[r] - lps[r], u)) {
-#pragma unroll
-                            for (int i = 0; i < KQ; i++) s[r][i] = p[r][i];
-                            lps[r] = lpp[r];
-                        }
+                        for (int i = 0; i < KQ; i++) s[i] = p[i];
+                        lps = lpp;
                     }
                 }
                 // the sub-chain's end point is the proposal; no fine evaluation for a chain that did
                 // not move (metropolisHastings.py:60-61).  The GEMM is warp wide: it runs when ANY of
-                // the 16 chains moved, and only the chains that moved use (and count) its result.
-                bool moved[2];
+                // the 8 chains moved, and only the chains that moved use (and count) its result.
+                bool same = true;
 #pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    bool same = true;
-#pragma unroll
-                    for (int i = 0; i < KQ; i++) same = same && (s[r][i] == TH(r, i));
-                    const unsigned m = __ballot_sync(0xffffffffu, same);
-                    moved[r] = (((m >> (4 * g)) & 0xFu) != 0xFu) && live[r];
-                }
-                if (__any_sync(0xffffffffu, moved[0] || moved[1])) {
-                    double lpf[2];
-                    logpost_tile<KQ>(Lv[1], ks, s, g, t, lpf[0], lpf[1]);
-#pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        const int64_t gg = live[r] ? gr[r] : 0;
-                        if (!moved[r]) continue;
+                for (int i = 0; i < KQ; i++) same = same && (s[i] == TH(i));
+                const unsigned m = __ballot_sync(0xffffffffu, same);
+                const bool moved = (((m >> (4 * g)) & 0xFu) != 0xFu) && live;
+                double lpf = 0.0;
+                if (__any_sync(0xffffffffu, moved)) {
+                    lpf = logpost_tile<KQ>(Lv[1], ks, s, g, t);
+                    if (moved) {
                         if (t == 0) cnt_ev1++;
                         double u;
-                        if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
+                        if (noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
                         else {
-                            u = philox_uniform(a.seed, (uint64_t)(a.chain_offset + gg), step, YG_SUB_FINE);
-                            if (a.noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
+                            u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                            if (noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
                         }
-                        const double delta = lpf[r] + lp0[r] - lps[r] - lp1[r];     // mlda.py:148-152, this order
-                        accepted[r] = accept_rule(delta, u);
-                    }
-                    welford_flush(accepted[0], accepted[1]);
-#pragma unroll
-                    for (int r = 0; r < 2; r++) {
-                        if (accepted[r]) {
-#pragma unroll
-                            for (int i = 0; i < KQ; i++) TH(r, i) = s[r][i];
-                            lp0[r] = lps[r];
-                            lp1[r] = lpf[r];
-                        }
+                        const double delta = lpf + lp0 - lps - lp1;     // mlda.py:148-152, this order
+                        accepted = accept_rule(delta, u);
                     }
                 }
-            }
+                welford_flush(accepted);
+                if (accepted) {
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (!live[r]) continue;
-                if (accepted[r]) { nacc[r]++; if (t == 0) cnt_acc++; }
+                    for (int i = 0; i < KQ; i++) TH(i) = s[i];
+                    lp0 = lps;
+                    lp1 = lpf;
+                }
+            }
+            if (live) {
+                if (accepted) { nacc++; if (t == 0) cnt_acc++; }
                 if (t == 0) {
                     cnt_tr++;
-                    if (a.accepted) a.accepted[n * N + gr[r]] = accepted[r] ? 1 : 0;
+                    if (a.accepted) a.accepted[n * N + gr] = accepted ? 1 : 0;
                 }
                 if ((n + 1) % a.thin == 0) {
                     const int64_t o = (n + 1) / a.thin - 1;
                     if (a.samples) {
-#pragma unroll
+#pragma unroll 1
                         for (int i = 0; i < KQ; i++)
-                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr[r]] = TH(r, i);
+                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr] = TH(i);
                     }
                     if (a.lp_out && t == 0) {
-                        a.lp_out[(o * n_lvl) * N + gr[r]] = lp0[r];
-                        if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + gr[r]] = lp1[r];
+                        a.lp_out[(o * n_lvl) * N + gr] = lp0;
+                        if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + gr] = lp1;
                     }
                 }
             }
         }
         // ---- store chain state ------------------------------------------------------------------
-        welford_flush(true, true);
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            if (!live[r]) continue;
-#pragma unroll
+        welford_flush(true);
+        if (live) {
+#pragma unroll 1
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
-                if (k < d) a.theta[(int64_t)k * N + gr[r]] = TH(r, i);
+                if (k < d) a.theta[(int64_t)k * N + gr] = TH(i);
             }
             if (t == 0) {
-                a.logpost[gr[r]] = lp0[r];
-                if (TWO_LEVEL) a.logpost[N + gr[r]] = lp1[r];
-                a.n_accept[gr[r]] = nacc[r];
+                a.logpost[gr] = lp0;
+                if (TWO_LEVEL) a.logpost[N + gr] = lp1;
+                a.n_accept[gr] = nacc;
             }
         }
     }
@@ -482,15 +439,18 @@ template <int KQ>
 int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
-    const size_t smem = sizeof(double) * ((((size_t)hh->tail_len + 1) & ~size_t(1)) + (size_t)8 * 16 * hh->ks);
-    auto kern = e->cfg.n_levels == 2 ? linear_dmma_mh_kernel<KQ, true> : linear_dmma_mh_kernel<KQ, false>;
+    const size_t smem = sizeof(double) * ((((size_t)hh->tail_len + 1) & ~size_t(1)) + (size_t)BIG_WARPS * 8 * hh->ks);
+    const bool free_noise = a.noise_mode == YG_NOISE_PHILOX;
+    auto kern = e->cfg.n_levels == 2
+                    ? (free_noise ? linear_dmma_mh_kernel<KQ, true, true> : linear_dmma_mh_kernel<KQ, true, false>)
+                    : (free_noise ? linear_dmma_mh_kernel<KQ, false, true> : linear_dmma_mh_kernel<KQ, false, false>);
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t tiles = (a.n_chains + 15) / 16;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + 7) / 8, e->sm_count));
-    kern<<<grid, 256, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem));
+    const int64_t tiles = (a.n_chains + 7) / 8;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BIG_WARPS - 1) / BIG_WARPS, e->sm_count));
+    kern<<<grid, BIG_WARPS * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem));
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
-    e->last_block = 256;
+    e->last_block = BIG_WARPS * 32;
     e->last_smem = (int)smem;
     e->launches += 1;
     return YG_OK;
