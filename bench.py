@@ -432,7 +432,7 @@ def measure_other_configs(device, fp64_peak):
     tpeak = fp64_tensor_peak_tflops(device, 20.0)
     out["linear_d64_x256_65536"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
                                     "fp64_tflops": fl / ms * 1e-9, "dmma_peak_tflops": tpeak, "frac_of_dmma_peak": fl / ms * 1e-9 / tpeak,
-                                    "kernel": "linear_dmma_mh_kernel<16,false>"}
+                                    "kernel": "linear_dmma_mh_kernel<16,false,true>"}
     ens.close()
     return out
 

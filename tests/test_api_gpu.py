@@ -237,6 +237,38 @@ def test_linear_two_level_through_builders_matches_closed_form():
     np.testing.assert_allclose(np.cov(x.T), cov, rtol=0.15, atol=5e-3)
 
 
+def test_large_linear_model_through_builders():
+    """d = 24, dataDim = 40 (beyond the one-chain-per-thread kernels): the builder path lands on the DMMA
+    kernel; posterior moments against the closed form, FullDiagnostics from the diagonal Welford state."""
+    meta, a = bp.big_linear_problem(24, 40, 2, two_level=True, J=2)
+    d, dd = 24, 40
+    noise = CentredGaussianNoise(IIDCovarianceMatrix(dd, 0.05))
+    prior = Gaussian(ParameterVector(np.zeros(d)), IIDCovarianceMatrix(d, 2.0))
+    lik = [AdditiveGaussianNoiseLikelihood(Data(a["L0_data"]), ForwardModel(LinearModelSolver(a[f"L{l}_G"], a[f"L{l}_b"])), noise)
+           for l in range(2)]
+    b = MLDABuilder()
+    b.bayesModel = BayesianRegressionModelHierarchy(Hierarchy(lik), SharedComponent(prior, 2))
+    b.baseProposalCovariance = IIDCovarianceMatrix(d, float(a["prop_L"][0, 0]) ** 2)
+    b.subChainLengths = [2]
+    b.targetDiagnostics = FullDiagnostics()
+    b.nChains, b.seed, b.thin = 2048, 3, 100
+    mc = b.build_method()
+    mean, cov = bp.linear_gaussian_posterior(a, 1)
+    mc.run(3001, ParameterVector(mean), verbose=False)
+    assert mc.ensemble.last_launch()["block"] == 512          # linear_dmma_mh_kernel (16 warps)
+    states = np.asarray(mc.chain.trajectory)
+    assert states.shape == (31, 2048, d)
+    x = states[11:].reshape(-1, d)
+    se = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(x.mean(0) - mean) < 0.05 * se + 5 * se / np.sqrt(2048))
+    np.testing.assert_allclose(x.var(0, ddof=1), np.diag(cov), rtol=0.1)
+    assert 0.1 < mc.diagnostics.global_acceptance_rate() < 0.8
+    np.testing.assert_allclose(mc.diagnostics.mean().mean(0), mean, atol=0.05)
+    assert mc.diagnostics.marginal_variance().shape == (2048, d)
+    lp = mc.target.evaluate_log(ParameterVector(mean))
+    assert np.isfinite(lp)
+
+
 def test_adaptive_error_model_through_builders():
     """example_inference_linearModel_twoLevel.py:95-102,183-191: AEM on the C3 linear pair lifts the fine
     acceptance rate (0.04 -> 0.35 in the reference's script) and still samples the fine posterior."""
