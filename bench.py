@@ -141,7 +141,7 @@ def run_reference_arm(args):
         "note": "the reference is pure Python (~40 chain-steps/s/core with an RK4 plugin, BASELINE.md); "
                 "it cannot travel to the GPU box, so this arm times the C port of the same algorithm",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -157,8 +157,6 @@ def run_gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -368,7 +366,7 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "launch": ens.last_launch(),
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -437,7 +435,26 @@ def measure_other_configs(device, fp64_peak):
     return out
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries (NCCL's version banner, for one) write to file descriptor 1
+    directly, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private copy of the
+    original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
