@@ -572,6 +572,84 @@ def case_postprocessing():
     arrays['dense_norm2'] = np.array([dc.induced_norm_squared(x) for x in v])
     save("postprocessing", dict(note='autocorrelation.py:5-140, estimation.py:36-53, covariance.py:69-94'), arrays)
 
+# --------------------------------------------------------------------------
+# long seeded runs of the UNMODIFIED reference (its own numpy RNG, no injection): posterior
+# moments / acceptance / IAT of C5 and C4, the Monte-Carlo pin north_star asks for; and the
+# forward map of the reference's shipped solver (test/testSetup.py:101-141, solve_ivp) at tight
+# tolerance, the accuracy pin of the RK4 replacement (style of test/test_solver_invoke.py:64-94)
+# --------------------------------------------------------------------------
+
+def _lv_long_worker(args):
+    twoLevel, seed, nSteps, burn = args
+    import numpy.random as npr
+    from yagremcmc.postprocessing.autocorrelation import integrated_autocorrelation
+    npr.seed(seed)                      # the reference draws from numpy's legacy global RNG
+    p = lv_problem()
+    likC, likF, prior = lv_models(p)
+    if twoLevel:
+        b = rh.MLDABuilder()
+        b.bayesModel = rh.BayesianRegressionModelHierarchy(
+            rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, 0.1)
+        b.subChainLengths = [3]
+    else:
+        b = rh.MRWBuilder()
+        b.bayesModel = rh.BayesianRegressionModel(likF, prior)
+        b.proposalCovariance = rh.IIDCovarianceMatrix(2, 0.15)
+    mcmc = rh.quiet(b.build_method)
+    rng = Generator(Philox(7000 + seed))
+    init = rh.LotkaVolterraParameter.from_coefficient(p['truth'] + 0.05 * rng.standard_normal(2))
+    rh.quiet(mcmc.run, nSteps, init, verbose=False)
+    traj = np.array([np.asarray(s, dtype=np.float64).reshape(-1) for s in mcmc.chain.trajectory])
+    iat = integrated_autocorrelation(traj[burn:], 'max')
+    return traj[burn:], mcmc.diagnostics.global_acceptance_rate(), iat
+
+
+def case_lv_long(twoLevel, nProc=8, nSteps=9000, burn=200):
+    import multiprocessing as mp
+    name = "lv_long_twoLevel" if twoLevel else "lv_long_singleLevel"
+    with mp.get_context("fork").Pool(nProc) as pool:
+        res = pool.map(_lv_long_worker, [(twoLevel, 100 + c, nSteps, burn) for c in range(nProc)])
+    chains = np.stack([r[0] for r in res])                       # [nProc, n, 2]
+    acc = np.array([r[1] for r in res]); iat = np.array([r[2] for r in res], dtype=np.float64)
+    flat = chains.reshape(-1, 2)
+    ess = float(sum(chains.shape[1] // max(int(t), 1) for t in iat))
+    arrays = dict(chain_means=chains.mean(axis=1), mean=flat.mean(axis=0), cov=np.cov(flat.T),
+                  acceptance=acc, iat=iat, ess=np.array(ess), n_kept=np.array(chains.shape[1]))
+    meta = dict(model='lv', levels=2 if twoLevel else 1, nChains=nProc, nSteps=nSteps, burnIn=burn,
+                note='unmodified reference chain stack + RK4 plugin, numpy legacy RNG seeded per chain; '
+                     'problem = lv_problem() (C5 / C4 constants)')
+    print(f"    {name}: mean {arrays['mean']}, acceptance {acc.mean():.3f}, IAT {iat}, ESS {ess:.0f}")
+    save(name, meta, arrays)
+
+
+def case_lv_forward():
+    """Forward map of the reference's own LotkaVolterraSolver (solve_ivp DOP853 at rtol 1e-12; the class
+    does not expose atol, so scipy's default 1e-6 bounds the accuracy) next to the RK4 plugin's, at the
+    truth and at a few posterior-scale points."""
+    from yagremcmc.test.testSetup import LotkaVolterraSolver
+    p = lv_problem()
+    cfg = dict(p['cfg'], T=p['cfg']['T'], solver='DOP853', rtol=1e-12)
+    thetas = np.stack([p['truth'], p['truth'] + [0.1, -0.08], p['truth'] + [-0.15, 0.12], [-0.5, -0.9]])
+    out_ref, out_rk4 = [], {64: [], 512: [], 1024: []}
+    for th in thetas:
+        prm = rh.LotkaVolterraParameter.from_coefficient(th)
+        sol = LotkaVolterraSolver(p['design'], cfg)
+        sol.interpolate(prm); sol.invoke()
+        out_ref.append(np.array(sol.evaluation))
+        for N in out_rk4:
+            s2 = rh.RK4LotkaVolterraSolver(p['design'], dict(p['cfg'], rk4Steps=N))
+            s2.interpolate(prm); s2.invoke()
+            out_rk4[N].append(s2.evaluation)
+    arrays = dict(thetas=thetas, design=p['design'], lv=np.array([0.8, 0.4, p['cfg']['T']]),
+                  ref_forward=np.stack(out_ref),
+                  **{f"rk4_{N}": np.stack(v) for N, v in out_rk4.items()})
+    for N in out_rk4:
+        e = np.abs(arrays[f"rk4_{N}"] - arrays['ref_forward']) / np.abs(arrays['ref_forward'])
+        print(f"    lv_forward: RK4 N={N} vs reference DOP853: max rel err {e.max():.3e}")
+    save("lv_forward", dict(model='lv', note='reference LotkaVolterraSolver (testSetup.py:101-141), '
+                            'DOP853 rtol 1e-12, vs the RK4 plugin'), arrays)
+
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
@@ -598,3 +676,8 @@ if __name__ == "__main__":
         cases_pcn()
     if want('aem'):
         cases_aem()
+    if want('lvforward'):
+        case_lv_forward()
+    if want('lvlong'):
+        case_lv_long(True)
+        case_lv_long(False)

@@ -536,6 +536,45 @@ def test_c5_full_size_properties():
     assert abs(c2["accepted"] / c2["fine_evals"] - 1.0) < 1e-3
 
 
+@pytest.mark.parametrize("two_level", [True, False])
+def test_lv_posterior_moments_match_long_reference_runs(two_level):
+    """north_star: posterior mean and covariance match long runs of the reference within Monte-Carlo
+    error.  Fixture: 8 seeded chains x 9,000 steps of the UNMODIFIED reference chain stack (its own
+    numpy RNG, no injection) on C5 / C4, written by oracle/make_golden.py case_lv_long.  The ensemble
+    (65,536 chains) has a negligible error of its own, so the tolerance is the reference run's:
+    5 standard errors of its mean (from the spread of the 8 chain means), 4 sqrt(2/ESS) on variances."""
+    meta_r, ref = load("lv_long_twoLevel" if two_level else "lv_long_singleLevel")
+    nc = 65536
+    meta, arrays = bp.lv_problem(two_level)
+    ens = _ens(meta, arrays, nc, seed=2024)
+    ens.set_state(bp.lv_initial_states(nc))
+    ens.run(150 if two_level else 400, samples=False)          # burn-in (IAT 4.3 / 17)
+    out = ens.run(60, samples=True, thin=20)
+    x = out["samples"].cpu().numpy().transpose(1, 0, 2).reshape(2, -1)     # 3 snapshots x 65,536 chains
+    se = ref["chain_means"].std(axis=0, ddof=1) / np.sqrt(ref["chain_means"].shape[0])
+    assert np.all(np.abs(x.mean(axis=1) - ref["mean"]) < 5.0 * se + 1e-3), (x.mean(axis=1), ref["mean"], se)
+    cov = np.cov(x)
+    rel = 4.0 * np.sqrt(2.0 / float(ref["ess"]))
+    np.testing.assert_allclose(np.diag(cov), np.diag(ref["cov"]), rtol=rel)
+    assert abs(cov[0, 1] - ref["cov"][0, 1]) < rel * np.sqrt(ref["cov"][0, 0] * ref["cov"][1, 1])
+    c = ens.counters()
+    rate = c["accepted"] / c["transitions"]
+    assert abs(rate - ref["acceptance"].mean()) < 5.0 * ref["acceptance"].std(ddof=1) / np.sqrt(8) + 2e-3
+
+
+def test_lv_forward_through_logpost_matches_reference_solver():
+    """log-posterior of the device RK4 model at the fixture's parameter points against the value
+    computed from the reference solver's forward output (DOP853, tests/golden/lv_forward.npz)."""
+    _, a = load("lv_forward")
+    meta, arrays = bp.lv_problem(True)
+    ens = _ens(meta, arrays, len(a["thetas"]), seed=1)
+    lp = ens.logpost(1, a["thetas"]).cpu().numpy()
+    for i, th in enumerate(a["thetas"]):
+        r = a["ref_forward"][i] - arrays["L1_data"]
+        want = -0.5 * np.sum(r * (r @ arrays["L1_noise_prec"].T)) - 0.5 * th @ arrays["L1_prior_prec"] @ th
+        assert abs(lp[i] - want) < 2e-3 * abs(want) + 2e-3, (i, lp[i], want)
+
+
 def test_c4_single_level_full_size():
     nc, ns = 65536, 10
     meta, arrays = bp.lv_problem(False)

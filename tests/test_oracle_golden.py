@@ -92,6 +92,26 @@ def test_iat_welford_dense_match_reference():
         np.testing.assert_allclose(np.dot(x, inv), n2, rtol=1e-12)
 
 
+def test_rk4_forward_matches_the_reference_solver():
+    """The RK4 forward map (north_star's replacement of scipy.solve_ivp) against the reference's OWN
+    LotkaVolterraSolver (test/testSetup.py:101-141; DOP853, rtol 1e-12, scipy's default atol 1e-6),
+    evaluated in the container by oracle/make_golden.py: the C oracle equals the numpy RK4 plugin to
+    rounding and the reference solver to 1e-4 (N = 64) / 2e-5 (N = 512) relative -- the style of
+    test/test_solver_invoke.py:64-94 (rtol 1e-3), tighter."""
+    import bench_problems as bp
+    _, a = load("lv_forward")
+    meta, arrays = bp.lv_problem(True)
+    np.testing.assert_array_equal(arrays["L0_design"], a["design"])
+    pb = cport.Problem(meta, arrays)
+    for i, th in enumerate(a["thetas"]):
+        Fc, Ff = cport.forward(pb, 0, th), cport.forward(pb, 1, th)
+        np.testing.assert_allclose(Fc, a["rk4_64"][i], rtol=1e-13)
+        np.testing.assert_allclose(Ff, a["rk4_512"][i], rtol=1e-13)
+        np.testing.assert_allclose(Fc, a["ref_forward"][i], rtol=1e-4)
+        np.testing.assert_allclose(Ff, a["ref_forward"][i], rtol=2e-5)
+        np.testing.assert_allclose(a["rk4_1024"][i], a["ref_forward"][i], rtol=2e-5)
+
+
 def test_philox_known_answers():
     """Random123 kat_vectors for philox4x32-10."""
     assert cport.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]

@@ -212,15 +212,15 @@ __global__ void __launch_bounds__(256, 4) rk4_peak_kernel(double *sink, int iter
     double x[4], y[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        r[i] = lv_rates(0.8, 0.4, 10.0, 512, b0 + 1e-3 * (threadIdx.x + i), d0 + 1e-3 * i);
+        r[i] = lv_rates(10.0 / 512, b0 + 1e-3 * (threadIdx.x + i), d0 + 1e-3 * i);
         x[i] = 1.0 + 1e-3 * threadIdx.x;
         y[i] = 0.8 + 1e-3 * i;
     }
-    const LvConsts k = lv_consts();
+    const LvStepConsts k = lv_step_consts(0.8, 0.4, 10.0 / 512);
 #pragma unroll 1
     for (int s = 0; s < iters; s++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) lv_rk4_step(r[i], k, x[i], y[i]);
+        for (int i = 0; i < 4; i++) lv_rk4_step(k, r[i], x[i], y[i]);
     }
     const double s = (x[0] + y[0]) + (x[1] + y[1]) + (x[2] + y[2]) + (x[3] + y[3]);
     if (s == 1.2345) sink[0] = s;
@@ -298,8 +298,8 @@ extern "C" int yg_fp64_peak(int32_t device, double ms, double *tflops_out)
     const int grid = sms * 4, threads = 256;
     double best = 0.0;
     for (int variant = 0; variant < 2; variant++) {
-        // FP64-pipe instructions per thread per iteration: 64 DFMA, or 4 RK4 steps x 30
-        const double per_iter = variant == 0 ? 64.0 : 120.0;
+        // FP64-pipe instructions per thread per iteration: 64 DFMA, or 4 RK4 steps x 20
+        const double per_iter = variant == 0 ? 64.0 : 80.0;
         int iters = 2048;
         float t = 0.f;
         // calibrate the iteration count to about `ms` per launch, then take the best of 5

@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 #include "common.cuh"
+#include "lv_model.cuh"
 
 struct RunArgs {
     const DevProblemHeader *problem;
@@ -35,10 +36,11 @@ struct RunArgs {
     // noise
     int32_t noise_mode, _pad;
     double *z, *u_c, *u_f;
-    // LV kernel: per-level step size and the two chain-independent scaled rates h*alpha, h*gamma.
+    // LV kernel: per-level step size and the chain-independent scaled rates (lv_model.cuh).
     // Passed by value so the integration loop reads them as constant-bank operands (a DFMA with
     // three vector-register sources issues slower than one with two + a constant operand).
-    double lv_h[2], lv_ha[2], lv_hg[2];
+    double lv_h[2];
+    LvStepConsts lv_k[2];
     // [0] transitions [1] accepted [2] level-0 evals [3] level-1 evals
     unsigned long long *counters;
 };

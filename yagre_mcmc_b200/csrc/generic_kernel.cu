@@ -85,10 +85,12 @@ YG_DEVFN double logpost_any(const DevProblemHeader *pb, int lvl, const double (&
         });
     } else {   // YG_MODEL_LV_RK4 (thread-per-parameter evaluation; the hot path is lv_kernel.cu)
         const double *design = tail + Lv.design_off;
-        const LvRates rates = lv_rates(Lv.alpha, Lv.gamma, Lv.T, Lv.rk4_steps, exp(t[0]), exp(t[D > 1 ? 1 : 0]));
+        const double h = Lv.T / (double)Lv.rk4_steps;
+        const LvStepConsts kc = lv_step_consts(Lv.alpha, Lv.gamma, h);
+        const LvRates rates = lv_rates(h, exp(t[0]), exp(t[D > 1 ? 1 : 0]));
         sum = np_stream_sum(nD, [&](int n) {
             double X = design[2 * n], Y = design[2 * n + 1];
-            lv_integrate(rates, Lv.rk4_steps, X, Y);
+            lv_integrate(kc, rates, Lv.rk4_steps, X, Y);
             lv_finite_or_inf(X, Y);
             const double r[2] = {X - data[2 * n], Y - data[2 * n + 1]};
             return quad_form<2>(Lv.noise_prec, 2, r, 2);

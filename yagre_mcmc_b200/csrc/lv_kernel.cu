@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     // predecessor left in sx/sy; the predecessor has a smaller queue index, so it was grabbed
     // earlier and never waits on anything later: the spin on segdone[item] cannot deadlock.
     // A batch never holds two segments of one item (batch size <= nItems).
-    auto eval_phase = [&](const int lvl, const int cur, const double h, const double ha, const double hg) {
+    auto eval_phase = [&](const int lvl, const int cur, const double h, const LvStepConsts &kc) {
         const DevLevel &Lv = pb->lvl[lvl];
         const int na = nact[cur];
         const int nD = Lv.n_data;
@@ -196,10 +196,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                 const int seg = fast_div(u, nItems, inv_items), it = u - seg * nItems;
                 const int n = fast_div(it, na, inv_na), ai = it - n * na;
                 const int c = lst[ai];
-                LvRates r;
-                r.ha = ha; r.hg = hg;
-                r.hb = h * CH(BETA, c);
-                r.hd = h * CH(DELTA, c);
+                const LvRates r = lv_rates(h, CH(BETA, c), CH(DELTA, c));
                 double x, y;
                 if (seg == 0) { x = design[2 * n]; y = design[2 * n + 1]; }
                 else {
@@ -209,9 +206,9 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                     x = sx[it]; y = sy[it];
                 }
 #ifdef YG_TIMERS
-                lv_integrate(r, a.thin == 7 ? 0 : min(seg_len, Nrk - seg * seg_len), x, y);   // thin == 7: overhead-only run
+                lv_integrate(kc, r, a.thin == 7 ? 0 : min(seg_len, Nrk - seg * seg_len), x, y);   // thin == 7: overhead-only run
 #else
-                lv_integrate(r, min(seg_len, Nrk - seg * seg_len), x, y);
+                lv_integrate(kc, r, min(seg_len, Nrk - seg * seg_len), x, y);
 #endif
                 if (seg + 1 < nSeg) {
                     sx[it] = x; sy[it] = y;
@@ -400,9 +397,9 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                 const long long dbg_nz = yg_clk();
                 dbg_t[2] += dbg_nz - tA;
 #endif
-                // two inlined copies so that h, h*alpha, h*gamma are constant-bank operands
-                if (TWO_LEVEL && j == J) eval_phase(1, cur, a.lv_h[1], a.lv_ha[1], a.lv_hg[1]);
-                else eval_phase(0, cur, a.lv_h[0], a.lv_ha[0], a.lv_hg[0]);
+                // two inlined copies so that h and the chain-independent rates are constant-bank operands
+                if (TWO_LEVEL && j == J) eval_phase(1, cur, a.lv_h[1], a.lv_k[1]);
+                else eval_phase(0, cur, a.lv_h[0], a.lv_k[0]);
 #ifdef YG_TIMERS
                 const long long dbg_ev = yg_clk();
                 dbg_t[3] += dbg_ev - dbg_nz;
@@ -543,8 +540,7 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     RunArgs args = a;
     for (int l = 0; l < e->cfg.n_levels; l++) {
         args.lv_h[l] = hp->lvl[l].T / (double)hp->lvl[l].rk4_steps;
-        args.lv_ha[l] = args.lv_h[l] * hp->lvl[l].alpha;
-        args.lv_hg[l] = args.lv_h[l] * hp->lvl[l].gamma;
+        args.lv_k[l] = lv_step_consts(hp->lvl[l].alpha, hp->lvl[l].gamma, args.lv_h[l]);
     }
     // <= 512 threads: up to 128 registers per thread (no spills in the owners' phases)
     auto kern = threads <= 512 ? (two ? lv_mh_kernel<true, 512> : lv_mh_kernel<false, 512>)
