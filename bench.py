@@ -150,7 +150,7 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem, fp64_peak_tflops, iat_ess
+    from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem, fp64_peak_tflops, iat_ess, rk4_loop_steps_per_s
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,17 +227,29 @@ def run_gpu_arm(args):
         bp.lv_flops_per_eval(meta["n_data"], meta["Nf"]) * fine_ev
     peak = fp64_peak_tflops(local, 30.0)
     achieved = flops / n_gpus / (total_ms_max * 1e-3) / 1e12          # per GPU
+    # RK4 steps per second of one GPU against (a) the instructions the kernel issues for them and (b) the bare
+    # integrator loop measured live: the stage-point RK4 step (lv_model.cuh) executes the 58 textbook flop of a
+    # step in 20 FP64-pipe instructions, six of which take 1.5 issue slots (three vector-register sources)
+    rk4_rate = flops / bp.LV_FLOP_PER_RK4_STEP / n_gpus / (total_ms_max * 1e-3)
+    loop_rate = rk4_loop_steps_per_s(local, 30.0)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "frac_note": "achieved counts SURVEY 8d's algorithmic (textbook) 58 flop per RK4 step; the kernel issues "
+                             "20 FP64 instructions (40 flop slots) for them, so frac can exceed 1 -- see executed / rk4_loop",
+                "executed": {"fp64_instr_per_rk4_step": 20, "issue_slots_per_rk4_step": 23,
+                             "tflops": rk4_rate * 40e-12, "frac": rk4_rate * 40e-12 / peak,
+                             "slot_frac": rk4_rate * 46e-12 / peak},
+                "rk4_loop": {"steps_per_s": rk4_rate, "bare_loop_steps_per_s": loop_rate, "frac": rk4_rate / loop_rate,
+                             "note": "whole MH kernel against nothing but lv_integrate at 1024 threads per SM"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full capture of this
-                # command, profiles/r01_lv_mh_kernel_ncu_full.csv): 5.87 MB + 0.30 MB; the algorithmic state
+                # command, profiles/r01_lv_mh_kernel_ncu_full.csv): 5.85 MB + 0.79 MB; the algorithmic state
                 # traffic is 96 B per chain per launch = 6.3 MB at 65,536 chains (written state stays in L2)
-                "traffic": 6.17e6 if (args.chains == CHAINS_PER_GPU) else None,
+                "traffic": 6.64e6 if (args.chains == CHAINS_PER_GPU) else None,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_lv_mh_kernel_ncu_full.csv",
                 "algorithmic_bytes_per_launch": 96.0 * args.chains,
                 "kernel": "lv_mh_kernel<true>", "launch_ms": total_ms_max / args.steps,
                 "algorithmic_flop_per_launch": flops / n_gpus / args.steps,
-                "peak_source": "yg_fp64_peak: DFMA / RK4-step micro-benchmarks measured live on this GPU (best of "
-                               "variants); MEASURED_PEAKS.json has no fp64 entry",
+                "peak_source": "yg_fp64_peak: DFMA micro-benchmarks (pure chains / two-source 30-instruction mix) measured "
+                               "live on this GPU, best of variants; MEASURED_PEAKS.json has no fp64 entry",
                 "forward_evals_per_transition": {"coarse": coarse_ev / units, "fine": fine_ev / units}}
 
     # ---- end to end through the public API: host theta0 in, host trajectory out ---------------------

@@ -173,6 +173,9 @@ def gauss2d_problem(prop_var=1.0):
     return meta, arrays
 
 
+LV_FLOP_PER_RK4_STEP = 58.0      # textbook (unfused) RK4 step of the 2-state system, SURVEY 8d
+
+
 def lv_flops_per_eval(n_data, N):
     """Algorithmic work of one forward evaluation: 58 flop per RK4 step per ODE."""
-    return 58.0 * n_data * N
+    return LV_FLOP_PER_RK4_STEP * n_data * N

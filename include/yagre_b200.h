@@ -39,6 +39,8 @@
  *                            chains; the host all-reduces them across GPUs (NCCL, torch.distributed)
  *   yg_logpost               DensityInterface.evaluate_log statistics/interface.py:6-10
  *   yg_fp64_peak             (new) DFMA micro-benchmark: the measured FP64 roofline denominator
+ *   yg_rk4_loop_rate         (new) bare RK4 integrator loop (the replacement of LotkaVolterraSolver.invoke,
+ *                            test/testSetup.py:109-141): ceiling of RK4 steps/s for the LV step kernel
  *
  * Conventions
  *   - All `*_dev` pointers are DEVICE pointers owned by the caller (PyTorch
@@ -230,6 +232,9 @@ int yg_split_moments(const double *samples_dev, int64_t n_samples, int32_t d, in
 
 /* Dependent-free DFMA chains on every SM for about `ms` milliseconds; returns TFLOP/s (FMA = 2). */
 int yg_fp64_peak(int32_t device, double ms, double *tflops_out);
+/* The bare LV RK4 integrator (one integration per thread, 1024 threads per SM, nothing else) for about
+ * `ms` milliseconds per launch; returns RK4 steps/s of the whole GPU. */
+int yg_rk4_loop_rate(int32_t device, double ms, double *steps_per_s_out);
 /* The same for the FP64 tensor path (independent m16n8k4 DMMA accumulator chains). */
 int yg_fp64_tensor_peak(int32_t device, double ms, double *tflops_out);
 

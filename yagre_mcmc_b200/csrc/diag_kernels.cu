@@ -206,24 +206,50 @@ __global__ void __launch_bounds__(256, 4) dfma_peak_kernel(double *sink, int ite
     if (s == 123.456) sink[0] = s;                      // keeps the chains live
 }
 
-__global__ void __launch_bounds__(256, 4) rk4_peak_kernel(double *sink, int iters, double b0, double d0)
+// FP64-pipe peak probe, second instruction mix: 30 DFMA/DMUL/DADD per iteration and lane, every one
+// with at most two vector-register sources (the third is a constant-bank operand), two independent
+// dependency chains -- the mix of the k-form RK4 step.  Measures the pipe, not a model.
+__global__ void __launch_bounds__(256, 4) mix_peak_kernel(double *sink, int iters, double b0, double d0, double ha,
+                                                          double hg)
 {
-    LvRates r[4];
-    double x[4], y[4];
+    double hb[4], hd[4], x[4], y[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        r[i] = lv_rates(10.0 / 512, b0 + 1e-3 * (threadIdx.x + i), d0 + 1e-3 * i);
+        hb[i] = b0 + 1e-6 * (threadIdx.x + i);
+        hd[i] = d0 + 1e-6 * i;
         x[i] = 1.0 + 1e-3 * threadIdx.x;
         y[i] = 0.8 + 1e-3 * i;
     }
-    const LvStepConsts k = lv_step_consts(0.8, 0.4, 10.0 / 512);
 #pragma unroll 1
     for (int s = 0; s < iters; s++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) lv_rk4_step(k, r[i], x[i], y[i]);
+        for (int i = 0; i < 4; i++) {
+            double kx = x[i] * fma(-hb[i], y[i], ha), ky = y[i] * fma(hd[i], x[i], -hg);
+            double xs = fma(0.5, kx, x[i]), ys = fma(0.5, ky, y[i]);
+            double ax = fma(0.125, kx, x[i]), ay = fma(0.125, ky, y[i]);
+            kx = xs * fma(-hb[i], ys, ha); ky = ys * fma(hd[i], xs, -hg);
+            xs = fma(0.5, kx, x[i]); ys = fma(0.5, ky, y[i]);
+            ax = fma(0.25, kx, ax); ay = fma(0.25, ky, ay);
+            kx = xs * fma(-hb[i], ys, ha); ky = ys * fma(hd[i], xs, -hg);
+            xs = x[i] + kx; ys = y[i] + ky;
+            ax = fma(0.25, kx, ax); ay = fma(0.25, ky, ay);
+            kx = xs * fma(-hb[i], ys, ha); ky = ys * fma(hd[i], xs, -hg);
+            x[i] = fma(0.125, kx, ax);
+            y[i] = fma(0.125, ky, ay);
+        }
     }
     const double s = (x[0] + y[0]) + (x[1] + y[1]) + (x[2] + y[2]) + (x[3] + y[3]);
     if (s == 1.2345) sink[0] = s;
+}
+
+// The bare RK4 integrator of lv_model.cuh (20 FP64 instructions per step), one integration per thread,
+// 1024 threads per SM like lv_mh_kernel: the ceiling of RK4 steps/s for the LV step kernel.
+__global__ void __launch_bounds__(1024, 1) rk4_loop_kernel(double *sink, int n_steps, double h, LvStepConsts kc)
+{
+    const LvRates r = lv_rates(h, 0.4 * (1.0 + 1e-3 * (threadIdx.x & 63)), 0.6 * (1.0 + 2e-3 * (threadIdx.x & 31)));
+    double x = 0.5 + (threadIdx.x & 15) / 16.0, y = 1.5 - (threadIdx.x & 7) / 8.0;
+    lv_integrate(kc, r, n_steps, x, y);
+    if (x + y == 1.2345) sink[0] = x;
 }
 
 }  // namespace
@@ -298,15 +324,15 @@ extern "C" int yg_fp64_peak(int32_t device, double ms, double *tflops_out)
     const int grid = sms * 4, threads = 256;
     double best = 0.0;
     for (int variant = 0; variant < 2; variant++) {
-        // FP64-pipe instructions per thread per iteration: 64 DFMA, or 4 RK4 steps x 20
-        const double per_iter = variant == 0 ? 64.0 : 80.0;
+        // FP64-pipe instructions per thread per iteration: 64 DFMA, or 4 x 30 of the two-source mix
+        const double per_iter = variant == 0 ? 64.0 : 120.0;
         int iters = 2048;
         float t = 0.f;
         // calibrate the iteration count to about `ms` per launch, then take the best of 5
         for (int rep = 0; rep < 7; rep++) {
             YG_CUDA_CHECK(cudaEventRecord(e0));
             if (variant == 0) dfma_peak_kernel<<<grid, threads>>>(sink, iters, 0.999999, 1e-9);
-            else rk4_peak_kernel<<<grid, threads>>>(sink, iters, 0.4, 0.6);
+            else mix_peak_kernel<<<grid, threads>>>(sink, iters, 0.4 * 10 / 512, 0.6 * 10 / 512, 0.8 * 10 / 512, 0.4 * 10 / 512);
             YG_CUDA_CHECK(cudaEventRecord(e1));
             YG_CUDA_CHECK(cudaEventSynchronize(e1));
             YG_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
@@ -319,5 +345,38 @@ extern "C" int yg_fp64_peak(int32_t device, double ms, double *tflops_out)
     cudaEventDestroy(e1);
     cudaFree(sink);
     *tflops_out = best;
+    return YG_OK;
+}
+
+extern "C" int yg_rk4_loop_rate(int32_t device, double ms, double *steps_per_s_out)
+{
+    if (!steps_per_s_out) return YG_ERR_INVALID;
+    YG_CUDA_CHECK(cudaSetDevice(device));
+    int sms = 0;
+    YG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double *sink = nullptr;
+    YG_CUDA_CHECK(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    YG_CUDA_CHECK(cudaEventCreate(&e0));
+    YG_CUDA_CHECK(cudaEventCreate(&e1));
+    const double h = 10.0 / 512;
+    const LvStepConsts kc = lv_step_consts(0.8, 0.4, h);
+    int n_steps = 4096;
+    double best = 0.0;
+    float t = 0.f;
+    for (int rep = 0; rep < 7; rep++) {
+        YG_CUDA_CHECK(cudaEventRecord(e0));
+        rk4_loop_kernel<<<sms, 1024>>>(sink, n_steps, h, kc);
+        YG_CUDA_CHECK(cudaEventRecord(e1));
+        YG_CUDA_CHECK(cudaEventSynchronize(e1));
+        YG_CUDA_CHECK(cudaEventElapsedTime(&t, e0, e1));
+        if (rep >= 2) best = std::max(best, (double)n_steps * sms * 1024.0 / (t * 1e-3));
+        if (rep < 2 && t > 0.f)
+            n_steps = 8 * (int)std::max(64.0, std::min(4.0e6, n_steps / 8 * (ms > 0 ? ms : 20.0) / t));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *steps_per_s_out = best;
     return YG_OK;
 }

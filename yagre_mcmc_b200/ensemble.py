@@ -343,6 +343,15 @@ def fp64_peak_tflops(device=0, ms=20.0):
     return out.value
 
 
+def rk4_loop_steps_per_s(device=0, ms=20.0):
+    """Bare LV RK4 integrator loop (nothing but lv_integrate, 1024 threads per SM): RK4 steps/s of the GPU,
+    the ceiling for lv_mh_kernel."""
+    lib = _lib.load()
+    out = C.c_double()
+    check(lib.yg_rk4_loop_rate(int(device), float(ms), C.byref(out)))
+    return out.value
+
+
 def fp64_tensor_peak_tflops(device=0, ms=20.0):
     """FP64 tensor-path (DMMA) micro-benchmark: the roofline denominator of the large linear model."""
     lib = _lib.load()
