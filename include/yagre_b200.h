@@ -37,6 +37,8 @@
  *                            ESS idiom example_inference_lotkaVolterra_twoLevel.py:117-118,132
  *   yg_pooled_stats          (new) sufficient statistics for pooled moments / R-hat, summed over local
  *                            chains; the host all-reduces them across GPUs (NCCL, torch.distributed)
+ *   yg_set_proposal_factor   (new) pooled proposal covariance; cf. AdaptiveMRWProposal.set_state
+ *                            chain/adaptive.py:55-60
  *   yg_logpost               DensityInterface.evaluate_log statistics/interface.py:6-10
  *   yg_fp64_peak             (new) DFMA micro-benchmark: the measured FP64 roofline denominator
  *   yg_rk4_loop_rate         (new) bare RK4 integrator loop (the replacement of LotkaVolterraSolver.invoke,
@@ -196,6 +198,13 @@ int yg_set_problem(yg_ensemble *e, const yg_problem *pb);
 /* theta0_dev[d, n_chains]; evaluates the log-posterior(s) of the initial state
  * and resets counters, Welford and the step index. */
 int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stream);
+
+/* Replaces the proposal factor L (host, [d, d] row-major, lower triangular, positive diagonal) for the
+ * following yg_run calls: every chain of an adaptive ensemble restarts from it, a non-adaptive ensemble
+ * uses it as is.  This is the hook for a POOLED proposal covariance (covariance of all chains of all GPUs,
+ * all-reduced by the host; the reference swaps a chain's proposal covariance in
+ * AdaptiveMRWProposal.set_state, chain/adaptive.py:55-60).  Refused for pCN (the factor is the prior's). */
+int yg_set_proposal_factor(yg_ensemble *e, const double *L_host, void *stream);
 
 /* n_steps transitions of every chain.  thin >= 1; n_steps % thin == 0 when samples are stored. */
 int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin,

@@ -575,6 +575,49 @@ def test_lv_forward_through_logpost_matches_reference_solver():
         assert abs(lp[i] - want) < 2e-3 * abs(want) + 2e-3, (i, lp[i], want)
 
 
+def test_pooled_proposal_covariance():
+    """Optional pooled proposal covariance (north_star): after a burn-in with the example's poor proposal
+    (1.0 I on a target with variances 2.4 / 0.7) the covariance pooled over all chains replaces it; the factor
+    is chol(2.4^2/d Sigma_target) within Monte-Carlo error, the chains keep sampling the same target, and the
+    C-ABI refuses factors that are not lower triangular / positive, and pCN ensembles."""
+    from yagre_mcmc_b200.parallel import pooled_proposal_covariance
+    nc = 4096
+    meta, arrays = bp.gauss2d_problem()
+    ens = _ens(meta, arrays, nc, seed=31)
+    ens.set_state(np.tile([1.0, 1.5], (nc, 1)))
+    ens.run(3000, samples=False)
+    c0 = ens.counters()
+    out = pooled_proposal_covariance(ens)
+    want = np.linalg.cholesky(2.4 * 2.4 / 2 * bp.GAUSS2D_COV)
+    np.testing.assert_allclose(out["prop_L"], want, rtol=0.05, atol=0.02)
+    ens.run(2000, samples=False)
+    c1 = ens.counters()
+    th = ens.state()["theta"].cpu().numpy()
+    se = np.sqrt(np.diag(bp.GAUSS2D_COV) / nc)
+    assert np.all(np.abs(th.mean(1) - bp.GAUSS2D_MEAN) < 4.5 * se)
+    np.testing.assert_allclose(np.cov(th), bp.GAUSS2D_COV, rtol=0.12, atol=0.03)
+    rate0 = c0["accepted"] / c0["transitions"]
+    rate1 = (c1["accepted"] - c0["accepted"]) / (c1["transitions"] - c0["transitions"])
+    assert 0.28 < rate1 < 0.42 and abs(rate1 - 0.35) < abs(rate0 - 0.35) + 0.02     # 2-D optimal scaling: ~0.35
+    # the same call on an adaptive ensemble restarts every chain's factor from the pooled one
+    ens_a = _ens(meta, arrays, 256, seed=32, adaptive=dict(idle=10 ** 9, collection=10 ** 9, refresh=1, eps=1e-4))
+    ens_a.set_state(np.tile([1.0, 1.5], (256, 1)))
+    ens_a.run(10, samples=False)
+    ens_a.set_proposal_factor(want)
+    ens_a.run(1, samples=False)
+    L = ens_a.state()["prop_L"].cpu().numpy()                      # [d, d, n]
+    np.testing.assert_array_equal(L, np.broadcast_to(want[:, :, None], L.shape))
+    with pytest.raises((ValueError, RuntimeError)):
+        ens.set_proposal_factor(np.array([[1.0, 0.5], [0.0, 1.0]]))
+    with pytest.raises((ValueError, RuntimeError)):
+        ens.set_proposal_factor(np.array([[1.0, 0.0], [0.0, -1.0]]))
+    metap, arraysp = bp.lv_pcn_problem()
+    ens_p = _ens(metap, arraysp, 64, seed=33)
+    ens_p.set_state(bp.lv_initial_states(64))
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ens_p.set_proposal_factor(np.eye(2))
+
+
 def test_c4_single_level_full_size():
     nc, ns = 65536, 10
     meta, arrays = bp.lv_problem(False)

@@ -14,7 +14,21 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from yagre_mcmc_b200.parallel import (shard_range, all_reduce_stats, moments_from_stats,
-                                      split_rhat_from_moments)
+                                      split_rhat_from_moments, pooled_proposal_covariance)
+
+
+class _RankEnsemble:
+    """Stands in for ChainEnsemble on CPU: the statistics vector of this rank's chains and a recorder for
+    the proposal factor (the device side, yg_pooled_stats / yg_set_proposal_factor, is covered by -m gpu)."""
+
+    def __init__(self, vec, d):
+        self._vec, self.dim, self.L = vec, d, None
+
+    def pooled_stats(self):
+        return self._vec.clone()
+
+    def set_proposal_factor(self, L):
+        self.L = np.array(L)
 
 
 def _free_port():
@@ -54,6 +68,9 @@ def _worker(rank, world, port, q):
         hm = torch.from_numpy(np.stack([xs[:, :half].mean(1).T, xs[:, half:2 * half].mean(1).T]))
         hv = torch.from_numpy(np.stack([xs[:, :half].var(1, ddof=1).T, xs[:, half:2 * half].var(1, ddof=1).T]))
         rh = split_rhat_from_moments(hm, hv, half)
+        ens = _RankEnsemble(torch.from_numpy(_stats_vector(x[lo:hi], 100 * (hi - lo) + rank)), x.shape[2])
+        pooled = pooled_proposal_covariance(ens, eps=1e-6)
+        out["prop_L"], out["prop_L_set"] = pooled["prop_L"], ens.L
         q.put((rank, lo, hi, out, rh))
     finally:
         dist.destroy_process_group()
@@ -88,4 +105,8 @@ def test_two_rank_pooling_equals_single_process():
         W = halves.var(axis=1, ddof=1).mean(0)
         B_over_n = halves.mean(axis=1).var(axis=0, ddof=1)
         np.testing.assert_allclose(rh, np.sqrt(((half - 1) / half * W + B_over_n) / W), rtol=1e-12)
+        # pooled proposal covariance: every rank installs chol(2.4^2/d (Sigma_pooled + eps I))
+        want = np.linalg.cholesky(2.4 * 2.4 / d * (np.cov(flat.T) + 1e-6 * np.eye(d)))
+        np.testing.assert_allclose(out["prop_L_set"], want, rtol=1e-9)
     np.testing.assert_array_equal(res[0][3]["mean"], res[1][3]["mean"])
+    np.testing.assert_array_equal(res[0][3]["prop_L_set"], res[1][3]["prop_L_set"])    # bitwise the same factor

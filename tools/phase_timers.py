@@ -38,6 +38,6 @@ for bps, thr, seg in [(1, 1024, 128)]:
     items_c, items_f = t[:, 0, 6], t[:, 0, 7]
     if not two:
         items_c, items_f = np.zeros_like(items_c), items_c
-    ideal = (items_c * Nc + items_f * Nf) * 30 / 32.0 * 2 / 4 * bps
+    ideal = (items_c * Nc + items_f * Nf) * 23 / 32.0 * 2 / 4 * bps     # 23 issue slots per RK4 step
     print(f"  ideal FP64-pipe cycles / CTA total: mean {np.mean(ideal / total[:, 0]):.4f}; vs slowest CTA {ideal.mean() / total.max():.4f}")
     ens.close()

@@ -80,6 +80,7 @@ SYMBOLS = {
     "yg_destroy": (C.c_int, [C.c_void_p]),
     "yg_set_problem": (C.c_int, [C.c_void_p, C.POINTER(YgProblem)]),
     "yg_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yg_set_proposal_factor": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "yg_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(YgOutputs), C.POINTER(YgNoise), C.c_void_p]),
     "yg_get_state": (C.c_int, [C.c_void_p, C.POINTER(YgState), C.c_void_p]),
     "yg_load_state": (C.c_int, [C.c_void_p, C.POINTER(YgState), C.c_int64, C.c_int64, C.c_void_p]),

@@ -504,6 +504,55 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
     return YG_OK;
 }
 
+// Replaces the proposal factor between launches (pooled proposal covariance across GPUs, north_star;
+// the reference's only hook for this is AdaptiveMRWProposal swapping its covariance, chain/adaptive.py:55-60).
+extern "C" int yg_set_proposal_factor(yg_ensemble *e, const double *L_host, void *stream)
+{
+    int rc = check_handle(e, true, false);
+    if (rc) return rc;
+    const int d = e->cfg.dim;
+    if (!L_host) {
+        yg_set_error("yg_set_proposal_factor: L is null");
+        return YG_ERR_INVALID;
+    }
+    for (int i = 0; i < d; i++)
+        for (int j = 0; j < d; j++) {
+            const double v = L_host[(size_t)i * d + j];
+            if (!std::isfinite(v) || (j > i && v != 0.0) || (i == j && !(v > 0.0))) {
+                yg_set_error("proposal factor must be finite, lower triangular with a positive diagonal");
+                return YG_ERR_INVALID;
+            }
+        }
+    cudaStream_t st = (cudaStream_t)stream;
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    if (e->big) {
+        if (!is_diagonal(L_host, d)) {
+            yg_set_error("large linear model: the proposal factor must be diagonal");
+            return YG_ERR_UNSUPPORTED;
+        }
+        DevBigHeader *h = reinterpret_cast<DevBigHeader *>(e->h_problem.data());
+        double *tail = reinterpret_cast<double *>(e->h_problem.data() + sizeof(DevBigHeader));
+        for (int k = 0; k < d; k++) tail[h->propL_off + k] = L_host[(size_t)k * d + k];
+        char *dst = reinterpret_cast<char *>(e->d_problem) + sizeof(DevBigHeader) + sizeof(double) * h->propL_off;
+        YG_CUDA_CHECK(cudaMemcpyAsync(dst, tail + h->propL_off, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+        return YG_OK;
+    }
+    DevProblemHeader *h = reinterpret_cast<DevProblemHeader *>(e->h_problem.data());
+    if (h->proposal != YG_PROPOSAL_MRW) {
+        yg_set_error("the proposal factor of a pCN chain is the prior's (pcn.py:23-35) and cannot be replaced");
+        return YG_ERR_UNSUPPORTED;
+    }
+    copy_mat(h->prop_L, L_host, d, d);
+    YG_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(e->d_problem) + offsetof(DevProblemHeader, prop_L), h->prop_L,
+                                  sizeof(h->prop_L), cudaMemcpyHostToDevice, st));
+    if (e->cfg.adaptive && e->prop_L) {
+        const size_t n = (size_t)e->cfg.n_chains;
+        broadcast_L_kernel<<<(int)std::min<size_t>((n + 127) / 128, 2048), 128, 0, st>>>(e->d_problem, e->prop_L, (int64_t)n);
+        YG_CUDA_CHECK(cudaGetLastError());
+    }
+    return YG_OK;
+}
+
 extern "C" int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin, const yg_outputs *out, const yg_noise *noise,
                       void *stream)
 {

@@ -155,6 +155,16 @@ class ChainEnsemble:
             check(self.lib.yg_set_state(self._h, C.c_void_p(soa.data_ptr()), self._stream()))
         return self
 
+    def set_proposal_factor(self, L):
+        """Replaces the proposal factor (lower triangular [d, d], proposal covariance = L L') for the following
+        runs; see parallel.pooled_proposal_covariance."""
+        Lh = np.ascontiguousarray(np.asarray(L, dtype=np.float64))
+        if Lh.shape != (self.dim, self.dim):
+            raise ValueError(f"proposal factor must be [{self.dim}, {self.dim}], got {Lh.shape}")
+        with torch.cuda.device(self.device):
+            check(self.lib.yg_set_proposal_factor(self._h, Lh.ctypes.data_as(C.c_void_p), self._stream()))
+        return self
+
     def run(self, n_steps, thin=1, samples=True, accepted=False, logpost=False, inject=None, record=False,
             samples_out=None):
         """Runs n_steps transitions of every chain.

@@ -57,6 +57,29 @@ def pooled_diagnostics(ensemble):
     return moments_from_stats(vec, ensemble.dim)
 
 
+def proposal_factor_from_covariance(cov, scale=None, eps=1e-8):
+    """Lower Cholesky factor of scale * (cov + eps I); scale defaults to the adaptive-Metropolis 2.4^2 / d
+    (the scaling of DESIGN.md section 5).  Host-side, d x d."""
+    cov = np.asarray(cov, dtype=np.float64)
+    d = cov.shape[0]
+    s = 2.4 * 2.4 / d if scale is None else float(scale)
+    return np.linalg.cholesky(s * (0.5 * (cov + cov.T) + eps * np.eye(d)))
+
+
+def pooled_proposal_covariance(ensemble, scale=None, eps=1e-8):
+    """Optional pooled proposal covariance (north_star): the covariance of ALL chains of ALL ranks, from the
+    same all-reduced sufficient statistics as the diagnostics (one all-reduce of 3 + 2d + 2d^2 doubles over
+    NCCL / NVLink), becomes the proposal covariance of every chain: L = chol(scale (Sigma_pooled + eps I)).
+    Every rank computes the same factor from the same reduced vector, so the ensemble stays reproducible
+    and invariant to the GPU count.  Call it between runs, after a burn-in: the Welford statistics it pools
+    cover the steps since the last set_state.  Returns the moments dict with the factor under 'prop_L'."""
+    out = pooled_diagnostics(ensemble)
+    L = proposal_factor_from_covariance(out['covariance'], scale, eps)
+    ensemble.set_proposal_factor(L)
+    out['prop_L'] = L
+    return out
+
+
 def split_rhat_from_moments(hm, hv, half):
     """Split-R-hat per coordinate from per-chain half moments hm, hv [2, d, n] (torch tensors on any
     device) of THIS rank; all-reduced over ranks when torch.distributed is initialised.  The two
