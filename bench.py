@@ -414,13 +414,24 @@ def measure_other_configs(device, fp64_peak):
                                        "fp64_tflops": fl / ms * 1e-9, "frac_of_fp64_peak": fl / ms * 1e-9 / fp64_peak,
                                        "kernel": "lv_mh_kernel<false>"}
     ens.close()
+    # C5 with the finer fine level SURVEY 8d asks to report as well: Nf = 1024
+    meta, arrays = bp.lv_problem(True, Nf=1024)
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5)
+    ens.set_state(bp.lv_initial_states(65536))
+    ms, c = timed(ens, 20)
+    fl = bp.lv_flops_per_eval(meta["n_data"], meta["Nc"]) * c["coarse_evals"] + \
+        bp.lv_flops_per_eval(meta["n_data"], meta["Nf"]) * c["fine_evals"]
+    out["C5_lv_two_level_Nf1024_65536"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                                           "fp64_tflops": fl / ms * 1e-9, "frac_of_fp64_peak": fl / ms * 1e-9 / fp64_peak,
+                                           "kernel": "lv_mh_kernel<true>"}
+    ens.close()
     # C3: linear two level (J = 5), 16,384 chains -- a few hundred FP64 instructions per step, launch / issue bound
     meta, arrays = bp.linear_problem(True)
     ens = ChainEnsemble(LoweredProblem(meta, arrays), 16384, device=device, seed=5)
     ens.set_state(np.zeros((16384, 2)))
     ms, c = timed(ens, 5000)
     out["C3_linear_two_level_16384"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
-                                        "kernel": "generic_mh_kernel<2,2,true>"}
+                                        "kernel": "generic_mh_kernel<2,2,true> (warp-specialised: producer / consumer warps)"}
     ens.close()
     # C2: 2-D Gaussian target, per-chain adaptive Metropolis, 4,096 chains
     meta, arrays = bp.gauss2d_problem()
@@ -430,7 +441,7 @@ def measure_other_configs(device, fp64_peak):
     ens.run(12000, samples=False)
     ms, c = timed(ens, 5000)
     out["C2_gauss2d_adaptive_4096"] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
-                                       "kernel": "generic_mh_kernel<2,2,false> (adaptive)"}
+                                       "kernel": "generic_mh_kernel<2,2,false> (adaptive; warp-specialised: producer / consumer warps)"}
     ens.close()
     # GEMM-sized linear model (SURVEY 8d variant): d = 64, dataDim = 256, 65,536 chains, FP64 tensor path
     meta, arrays = bp.big_linear_problem(64, 256, 1)

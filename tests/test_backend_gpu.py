@@ -575,6 +575,44 @@ def test_lv_forward_through_logpost_matches_reference_solver():
         assert abs(lp[i] - want) < 2e-3 * abs(want) + 2e-3, (i, lp[i], want)
 
 
+@pytest.mark.parametrize("case", ["gauss2d", "gauss2d_adaptive", "linear_single_level", "linear_two_level", "gauss1d_isclose"])
+def test_warp_specialised_small_ensemble_kernel_is_bit_identical(case):
+    """Ensembles of <= 32,768 chains with d <= 2 and Philox noise run the warp-specialised variant of the
+    one-chain-per-thread kernel (producer warp draws the noise into a shared-memory ring, consumer warp runs
+    the state-dependent half).  Record mode always runs the plain kernel, which the Philox-replay tests pin to
+    the oracle: samples, decisions, counters and the whole chain state must agree bit for bit, including a
+    ragged last warp, one chain, thinning and a continued run."""
+    am = None
+    if case == "gauss2d":
+        (meta, arrays), init = bp.gauss2d_problem(), lambda n: np.tile([-8.0, -7.0], (n, 1))
+    elif case == "gauss2d_adaptive":
+        (meta, arrays), init = bp.gauss2d_problem(), lambda n: np.tile([-8.0, -7.0], (n, 1))
+        am = dict(idle=20, collection=30, refresh=3, eps=1e-4)
+    elif case == "gauss1d_isclose":
+        meta, a = load("mrw_gauss1d")
+        arrays = {k: v for k, v in a.items() if k.startswith("L0_") or k == "prop_L"}
+        init = lambda n: np.full((n, 1), -3.0)
+    else:
+        (meta, arrays), init = bp.linear_problem(case == "linear_two_level"), lambda n: np.zeros((n, 2))
+    for nc in (1, 333):
+        res = []
+        for record in (False, True):
+            ens = _ens(meta, arrays, nc, seed=77, adaptive=am)
+            ens.set_state(init(nc))
+            o1 = ens.run(120, samples=True, accepted=True, logpost=True, thin=3, record=record)
+            o2 = ens.run(37, samples=True, accepted=True, record=record)          # continues (step index, Welford)
+            launch = ens.last_launch()
+            res.append((o1, o2, ens.counters(), ens.state(), launch))
+        assert res[0][4]["block"] == 64 and res[1][4]["block"] == 128          # specialised vs plain kernel
+        for k in ("samples", "accepted", "logpost"):
+            assert torch.equal(res[0][0][k], res[1][0][k]), k
+        assert torch.equal(res[0][1]["samples"], res[1][1]["samples"])
+        assert res[0][2] == res[1][2]
+        for k, v in res[0][3].items():
+            if torch.is_tensor(v):
+                assert torch.equal(v, res[1][3][k]), k
+
+
 def test_pooled_proposal_covariance():
     """Optional pooled proposal covariance (north_star): after a burn-in with the example's poor proposal
     (1.0 I on a target with variances 2.4 / 0.7) the covariance pooled over all chains replaces it; the factor
@@ -675,10 +713,13 @@ def test_c2_gaussian_target_moments():
 # edge cases: smallest / largest / ragged sizes
 # ------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("shape", ["one_chain", "one_design_point", "one_rk4_step", "j1", "many_design_points"])
+@pytest.mark.parametrize("shape", ["one_chain", "one_design_point", "one_rk4_step", "j1", "many_design_points",
+                                   "long_observation_grid"])
 def test_lv_edge_shapes_against_oracle(shape):
     kw = dict(one_chain=dict(), one_design_point=dict(n_data=1), one_rk4_step=dict(Nc=1, Nf=3),
-              j1=dict(J=1), many_design_points=dict(n_data=37, Nc=8, Nf=24))[shape]
+              j1=dict(J=1), many_design_points=dict(n_data=37, Nc=8, Nf=24),
+              # > 128 design points: numpy's pairwise summation blocks (np_pairwise_sum), 8 chains per CTA chunk
+              long_observation_grid=dict(n_data=300, Nc=4, Nf=12, prop_var=2e-4))[shape]
     nc = 1 if shape == "one_chain" else 97
     meta, arrays = bp.lv_problem(True, **({"Nc": 16, "Nf": 48} | kw))
     th0 = bp.lv_initial_states(nc)

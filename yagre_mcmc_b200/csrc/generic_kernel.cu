@@ -27,11 +27,23 @@
 namespace {
 
 // numpy-ordered streaming sum of q_0..q_{n-1} produced by `next(i)` (np.sum, n <= 128 exact)
-template <typename F>
+// UNROLL_SMALL: for n < 8 the terms are evaluated as seven independent (predicated) copies before they are
+// added in the same order -- the dependent shared-memory loads and FP64 chains of the rows overlap instead of
+// running one row after the other (one chain per thread has nothing else to hide them behind).
+template <bool UNROLL_SMALL = false, typename F>
 YG_DEVFN double np_stream_sum(int n, F next)
 {
     if (n < 8) {
         double res = 0.0;
+        if (UNROLL_SMALL) {
+            double v[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) v[i] = (i < n) ? next(i) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 7; i++)
+                if (i < n) res += v[i];
+            return res;
+        }
         for (int i = 0; i < n; i++) res += next(i);
         return res;
     }
@@ -77,7 +89,7 @@ YG_DEVFN double logpost_any(const DevProblemHeader *pb, int lvl, const double (&
             }
             F[k] = acc;
         }
-        sum = np_stream_sum(nD, [&](int n) {
+        sum = np_stream_sum<true>(nD, [&](int n) {
             double r[DD];
 #pragma unroll
             for (int k = 0; k < DD; k++) r[k] = (k < dd) ? F[k] - data[n * dd + k] : 0.0;
@@ -156,10 +168,30 @@ YG_DEVFN bool cholesky_lower(const double (&C)[D][D], double (&L)[D][D], int d)
     return true;
 }
 
-template <int D, int DD, bool TWO_LEVEL>
-__global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
+// Warp-specialised variant (WS, d <= 2, Philox noise, small ensembles).  An ensemble of a few thousand
+// chains leaves most SM sub-partitions without a warp, and a chain step is one long dependent sequence
+// (Philox rounds -> log / sqrt / sincospi of Box-Muller -> proposal -> log-posterior -> exp -> compare): with
+// one warp per sub-partition nothing hides its latency.  The noise does not depend on the chain state
+// (counter-based Philox, keyed by chain / step / sub-step), so a CTA of three warps splits the sequence:
+// warps 1 and 2 PRODUCE the normals and uniforms of the coming sub-steps into a shared-memory ring, warp 0
+// CONSUMES them and runs only the state-dependent half.  Same streams, same arithmetic: trajectories are
+// bit-identical to the unspecialised kernel (tests/test_backend_gpu.py).
+constexpr int WS_RING = 16;                // ring entries; one entry = (z0, z1, u) of one sub-step for 32 chains
+constexpr int WS_THREADS = 64;             // 1 consumer warp + 1 producer warp (more producers measured no gain)
+constexpr int64_t WS_MAX_CHAINS = 32768;   // beyond this the plain kernel has enough warps per sub-partition
+
+template <int D, int DD, bool TWO_LEVEL, bool WS>
+__global__ void __launch_bounds__(256) generic_mh_kernel(const RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ws_ring = nullptr;
+    volatile unsigned long long *ws_ready = nullptr, *ws_consumed = nullptr;
+    if (WS) {
+        ws_ring = reinterpret_cast<double *>(smem_raw + ((a.problem_bytes + 15u) & ~15u));       // [WS_RING][3][32]
+        ws_ready = reinterpret_cast<volatile unsigned long long *>(ws_ring + WS_RING * 96);     // [WS_RING]
+        ws_consumed = ws_ready + WS_RING;
+        if (threadIdx.x <= WS_RING) ws_ready[threadIdx.x] = 0ull;                               // incl. ws_consumed
+    }
     stage_blob(smem_raw, a.problem, a.problem_bytes);
     const DevProblemHeader *pb = reinterpret_cast<const DevProblemHeader *>(smem_raw);
     const int d = pb->dim;
@@ -170,7 +202,53 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
     const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
 
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < N; g += (int64_t)gridDim.x * blockDim.x) {
+    const int ws_lane = threadIdx.x & 31;
+    const int ws_per_step = TWO_LEVEL ? J + 1 : 1;       // ring entries per transition
+    if (WS && threadIdx.x >= 32) {
+        // ---- producer warps: entry q = (transition n, sub-step j); warp w fills q = w, w + 2, ... ----
+        const uint64_t gid = (uint64_t)(a.chain_offset + blockIdx.x * 32ll + ws_lane);
+        const unsigned long long Q = (unsigned long long)a.n_steps * (unsigned long long)ws_per_step;
+        const unsigned n_prod = (blockDim.x >> 5) - 1;
+        int64_t n = 0;
+        int j = (int)(threadIdx.x >> 5) - 1;                  // (n, j) = divmod(q, ws_per_step), kept incrementally
+        for (unsigned long long q = (threadIdx.x >> 5) - 1; q < Q; q += n_prod, j += (int)n_prod) {
+            while (j >= ws_per_step) { j -= ws_per_step; n++; }
+            while (*ws_consumed + WS_RING <= q) __nanosleep(20);
+            const uint64_t step = (uint64_t)(a.step0 + n);
+            double z0 = 0.0, z1 = 0.0, u;
+            if (!TWO_LEVEL || j < J) philox_normal_pair(a.seed, gid, step, (uint32_t)j, 0u, z0, z1);
+            u = philox_uniform(a.seed, gid, step, (!TWO_LEVEL || j == J) ? YG_SUB_FINE : (uint32_t)j);
+            double *slot = ws_ring + (q % WS_RING) * 96 + ws_lane;
+            slot[0] = z0; slot[32] = z1; slot[64] = u;
+            __threadfence_block();
+            __syncwarp();
+            if (ws_lane == 0) ws_ready[q % WS_RING] = q + 1ull;
+        }
+        return;
+    }
+    unsigned ws_mask = 0xffffffffu;
+    unsigned long long ws_q = 0ull;
+    double ws_z0 = 0.0, ws_z1 = 0.0, ws_u = 0.0;
+    // consumer: the noise of ring entry ws_q (all live lanes of the warp call this together)
+    auto ws_fetch = [&]() {
+        __syncwarp(ws_mask);
+        const int e = (int)(ws_q % WS_RING);
+        while (ws_ready[e] != ws_q + 1ull) { }
+        __threadfence_block();
+        const volatile double *slot = ws_ring + e * 96 + ws_lane;
+        ws_z0 = slot[0]; ws_z1 = slot[32]; ws_u = slot[64];
+        __syncwarp(ws_mask);
+        ws_q += 1ull;
+        if (ws_lane == __ffs(ws_mask) - 1) *ws_consumed = ws_q;
+    };
+    if (WS) {
+        ws_mask = __ballot_sync(0xffffffffu, blockIdx.x * 32ll + ws_lane < N);
+        if (blockIdx.x * 32ll + ws_lane >= N) return;
+    }
+
+    const int64_t g_first = WS ? blockIdx.x * 32ll + ws_lane : blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t g_stride = WS ? N : (int64_t)gridDim.x * blockDim.x;      // WS: one chain per consumer lane
+    for (int64_t g = g_first; g < N; g += g_stride) {
         const uint64_t gid = (uint64_t)(a.chain_offset + g);
         double th[D], wm[D], w2[D][D], L[D][D];
         double am_m[D], am_2[D][D];
@@ -200,7 +278,10 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
         // p = s + L z, unfused, exact zeros of L skipped (covariance.py:51-52,84-86)
         auto propose = [&](const double (&s)[D], int64_t n, int j, uint64_t step, double (&p)[D]) {
             double z[D];
-            if (a.noise_mode == YG_NOISE_INJECT) {
+            if (WS) {
+#pragma unroll
+                for (int i = 0; i < D; i++) z[i] = (i == 0) ? ws_z0 : (i == 1 ? ws_z1 : 0.0);
+            } else if (a.noise_mode == YG_NOISE_INJECT) {
 #pragma unroll
                 for (int i = 0; i < D; i++) z[i] = (i < d) ? a.z[((n * J + j) * d + i) * N + g] : 0.0;
             } else {
@@ -242,6 +323,7 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
             }
         };
 
+        int64_t thin_left = a.thin, thin_out = 0;
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
             // ---- diagnostics Welford of the pre-transition state (diagnostics.py:91-94) ----
@@ -275,7 +357,7 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
                     for (int i = 0; i < D; i++)
 #pragma unroll
                         for (int j = 0; j < D; j++) am_2[i][j] += dl[i] * e[j];
-                    if (n_am >= a.am_collect && n_am >= 2 && ((n_am - a.am_collect) % a.am_refresh) == 0) {
+                    if (n_am >= a.am_collect && n_am >= 2 && (a.am_refresh == 1 || ((n_am - a.am_collect) % a.am_refresh) == 0)) {
                         double Cm[D][D], Ln[D][D];
 #pragma unroll
                         for (int i = 0; i < D; i++)
@@ -298,12 +380,14 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
             bool accepted = false;
             if (!TWO_LEVEL) {
                 double p[D];
+                if (WS) ws_fetch();
                 propose(th, n, 0, step, p);
                 if (!equal(p, th)) {                                    // metropolisHastings.py:60-61
                     const double lpp = logpost_any<D, DD>(pb, 0, p);
                     cnt_ev0++;
                     double u;
-                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
+                    if (WS) u = ws_u;
+                    else if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
                     else {
                         u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
                         if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
@@ -321,13 +405,15 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
                 for (int i = 0; i < D; i++) s[i] = th[i];
                 double lps = lp0;
                 for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
+                    if (WS) ws_fetch();
                     propose(s, n, j, step, p);
                     if (equal(p, s)) continue;
                     const double lpp = logpost_any<D, DD>(pb, 0, p);
                     cnt_ev0++;
                     double u;
                     const int64_t ui = (n * J + j) * N + g;
-                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
+                    if (WS) u = ws_u;
+                    else if (a.noise_mode == YG_NOISE_INJECT) u = a.u_c[ui];
                     else {
                         u = philox_uniform(a.seed, gid, step, (uint32_t)j);
                         if (a.noise_mode == YG_NOISE_RECORD) a.u_c[ui] = u;
@@ -338,11 +424,13 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
                         lps = lpp;
                     }
                 }
+                if (WS) ws_fetch();
                 if (!equal(s, th)) {
                     const double lpf_s = logpost_any<D, DD>(pb, 1, s);
                     cnt_ev1++;
                     double u;
-                    if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
+                    if (WS) u = ws_u;
+                    else if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
                     else {
                         u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
                         if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
@@ -360,8 +448,9 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
             if (accepted) { nacc++; cnt_acc++; }
             cnt_tr++;
             if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
-            if ((n + 1) % a.thin == 0) {
-                const int64_t o = (n + 1) / a.thin - 1;
+            if (--thin_left == 0) {                 // (n + 1) % thin == 0 without a 64-bit division per step
+                thin_left = a.thin;
+                const int64_t o = thin_out++;
                 if (a.samples) {
 #pragma unroll
                     for (int i = 0; i < D; i++)
@@ -401,6 +490,10 @@ __global__ void __launch_bounds__(128) generic_mh_kernel(const RunArgs a)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
 #pragma unroll
+        if (WS) {                                   // exited lanes (chains beyond N, producers) cannot shuffle
+            if (v[k]) atomicAdd(&a.counters[k], v[k]);
+            continue;
+        }
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
     }
@@ -641,6 +734,7 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
             return eq;
         };
 
+        int64_t thin_left = a.thin, thin_out = 0;
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
             {   // diagnostics Welford of the pre-transition state (diagnostics.py:91-94)
@@ -719,8 +813,9 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
             if (accepted) { nacc++; cnt_acc++; }
             cnt_tr++;
             if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
-            if ((n + 1) % a.thin == 0) {
-                const int64_t o = (n + 1) / a.thin - 1;
+            if (--thin_left == 0) {                 // (n + 1) % thin == 0 without a 64-bit division per step
+                thin_left = a.thin;
+                const int64_t o = thin_out++;
                 if (a.samples) {
 #pragma unroll
                     for (int i = 0; i < D; i++)
@@ -798,11 +893,20 @@ int cap_of(int n)
 template <int D, int DD>
 int launch_generic_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
-    const int threads = 128;
+    int threads = 128;
     const int64_t want = (a.n_chains + threads - 1) / threads;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
-    const size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
-    auto kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true> : generic_mh_kernel<D, DD, false>;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
+    size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
+    auto kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true, false> : generic_mh_kernel<D, DD, false, false>;
+    // small ensembles with Philox noise: warp-specialised variant (see WS above); the parity modes
+    // (injected / recorded noise) stay on the plain kernel, which the WS variant equals bit for bit
+    if (D == 2 && a.noise_mode == YG_NOISE_PHILOX && a.n_chains <= WS_MAX_CHAINS && a.n_steps > 0) {
+        kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true, D == 2> : generic_mh_kernel<D, DD, false, D == 2>;
+        threads = WS_THREADS;
+        if (const char *np = getenv("YG_WS_PRODUCERS")) threads = 32 * (1 + std::max(1, std::min(7, atoi(np))));   // dev knob
+        grid = (int)((a.n_chains + 31) / 32);
+        smem += sizeof(double) * WS_RING * 96 + sizeof(unsigned long long) * (WS_RING + 1);
+    }
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, st>>>(a);
     YG_CUDA_CHECK(cudaGetLastError());
@@ -828,6 +932,13 @@ int launch_logpost_t(yg_ensemble *e, int level, const double *theta, int64_t n, 
     return YG_OK;
 }
 
+#ifdef YG_DEV_22      /* dev build (make dev): d, data_dim <= 2 only, compiles in a minute */
+#define YG_DISPATCH(FN, ...)                                                  \
+    switch (cd * 16 + cdd) {                                                   \
+    case 2 * 16 + 2: return FN<2, 2>(__VA_ARGS__);                             \
+    default: break;                                                            \
+    }
+#else
 #define YG_DISPATCH(FN, ...)                                                  \
     switch (cd * 16 + cdd) {                                                   \
     case 2 * 16 + 2: return FN<2, 2>(__VA_ARGS__);                             \
@@ -841,6 +952,7 @@ int launch_logpost_t(yg_ensemble *e, int level, const double *theta, int64_t n, 
     case 8 * 16 + 8: return FN<8, 8>(__VA_ARGS__);                             \
     default: break;                                                            \
     }
+#endif
 
 }  // namespace
 
