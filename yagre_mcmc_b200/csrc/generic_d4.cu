@@ -1,0 +1,5 @@
+// generic_d4.cu -- the one-chain-per-thread kernels (generic_kernel.cuh) for parameter-dimension capacity 4.
+#ifndef YG_DEV_22       /* the dev build (make dev) covers d <= 2 only */
+#include "generic_kernel.cuh"
+YG_GENERIC_UNIT(4)
+#endif
