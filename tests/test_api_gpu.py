@@ -80,6 +80,31 @@ def test_mcmc_2d_ensemble(proposal):
     assert iat.shape == (256,) and np.all(iat >= 1)
 
 
+def test_pooled_proposal_covariance_through_the_builder():
+    """Burn-in restart idiom of the reference (example_inference_linearModel_twoLevel.py:228,236) with the
+    pooled proposal covariance in between: burn-in from a far start with a small iid proposal, pool, restart
+    from chain.trajectory[-1]."""
+    tgtMean = np.array([1.0, 1.5])
+    tgtCov = np.array([[2.4, -0.5], [-0.5, 0.7]])
+    b = MRWBuilder()
+    b.explicitTarget = GaussianTargetDensity2d(ParameterVector(tgtMean), tgtCov)
+    b.proposalCovariance = IIDCovarianceMatrix(2, 0.02)
+    b.nChains, b.seed = 512, 9
+    mc = b.build_method()
+    mc.run(3000, ParameterVector(np.array([0.0, 0.0])), verbose=False)
+    rate0 = mc.diagnostics.global_acceptance_rate()
+    pooled = mc.pool_proposal_covariance()
+    L = pooled["prop_L"]
+    assert L.shape == (2, 2) and L[0, 1] == 0.0
+    last = np.asarray(mc.chain.trajectory)[-1]                                      # [nChains, d]
+    mc.run(3000, ParameterVector(last), verbose=False)
+    rate1 = mc.diagnostics.global_acceptance_rate()
+    assert rate0 > 0.7 and 0.25 < rate1 < 0.45                                      # tiny steps -> tuned steps
+    x = np.asarray(mc.chain.trajectory)[500:].reshape(-1, 2)
+    assert np.all(np.abs(x.mean(0) - tgtMean) < 5e-2)
+    assert np.all(np.abs(np.cov(x.T) - tgtCov) < 1e-1)
+
+
 def _mlda_targets(surrMeanShift, surrCov):
     tgtMean = ParameterVector(np.array([1.0, 1.5]))
     tgtCov = np.array([[2.5, -0.3], [-0.3, 0.9]])

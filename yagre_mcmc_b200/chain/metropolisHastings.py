@@ -146,3 +146,12 @@ class MetropolisHastings:
         """Pooled moments and R-hat over ALL chains (all ranks): see yagre_mcmc_b200.parallel."""
         from ..parallel import pooled_diagnostics
         return pooled_diagnostics(self._ensemble)
+
+    def pool_proposal_covariance(self, scale=None, eps=1e-8):
+        """Optional pooled proposal covariance: replaces the proposal covariance of every chain (all ranks) by
+        scale * (covariance pooled over all chains since the last run() started + eps I), scale = 2.4^2 / d by
+        default.  The idiom mirrors the reference's burn-in restart
+        (example_inference_linearModel_twoLevel.py:228,236): run a burn-in, pool, run again from
+        chain.trajectory[-1].  Returns the pooled moments with the new factor under 'prop_L'."""
+        from ..parallel import pooled_proposal_covariance
+        return pooled_proposal_covariance(self._ensemble, scale, eps)

@@ -25,7 +25,6 @@
 #include "lv_model.cuh"
 #include <math_constants.h>
 #include <algorithm>
-#include <cstdlib>
 
 namespace {
 
@@ -901,7 +900,6 @@ int launch_generic_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     if (D == 2 && a.noise_mode == YG_NOISE_PHILOX && a.n_chains <= WS_MAX_CHAINS && a.n_steps > 0) {
         kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true, D == 2> : generic_mh_kernel<D, DD, false, D == 2>;
         threads = WS_THREADS;
-        if (const char *np = getenv("YG_WS_PRODUCERS")) threads = 32 * (1 + std::max(1, std::min(7, atoi(np))));   // dev knob
         grid = (int)((a.n_chains + 31) / 32);
         smem += sizeof(double) * WS_RING * 96 + sizeof(unsigned long long) * (WS_RING + 1);
     }

@@ -265,8 +265,11 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
             return ((m >> (4 * g)) & 0xFu) == 0xFu;
         };
 
+        int64_t thin_left = a.thin, thin_out = -1;
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
+            const bool store_now = (--thin_left == 0);     // (n + 1) % thin == 0 without a 64-bit division per step
+            if (store_now) { thin_left = a.thin; thin_out++; }
             // FullDiagnostics: Welford of the pre-transition state (diagnostics.py:91-94): the state of
             // this step is seen once more; the accumulators are touched when the state changes.
             run += 1.0;
@@ -350,8 +353,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                     cnt_tr++;
                     if (a.accepted) a.accepted[n * N + gr] = accepted ? 1 : 0;
                 }
-                if ((n + 1) % a.thin == 0) {
-                    const int64_t o = (n + 1) / a.thin - 1;
+                if (store_now) {
+                    const int64_t o = thin_out;
                     if (a.samples) {
 #pragma unroll 1
                         for (int i = 0; i < KQ; i++)

@@ -300,8 +300,12 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
         }
         unsigned long long my_acc = 0ull;
 
+        int64_t thin_left = a.thin, thin_out = -1;
         for (int64_t n = 0; n < a.n_steps; n++) {
             const double wn = (double)(a.welford_n0 + n + 1);
+            // (n + 1) % thin == 0 without a 64-bit division per transition
+            const bool store_now = (--thin_left == 0);
+            if (store_now) { thin_left = a.thin; thin_out++; }
             // Phases j = 0..J-1: decide sub-step j-1, propose sub-step j, evaluate level 0.
             // Two level only, phase j = J: decide sub-step J-1, evaluate level 1 where the
             // sub-chain moved.  Then the commit below decides the transition.
@@ -437,8 +441,8 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                 }
                 if (accepted) { nacc[c] += 1ull; my_acc += 1ull; }
                 if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
-                if ((n + 1) % a.thin == 0) {
-                    const int64_t o = (n + 1) / a.thin - 1;
+                if (store_now) {
+                    const int64_t o = thin_out;
                     if (a.samples) {
                         a.samples[(o * LV_D) * N + g] = CH(TH0, c);
                         a.samples[(o * LV_D + 1) * N + g] = CH(TH1, c);
