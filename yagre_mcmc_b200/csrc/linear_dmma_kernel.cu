@@ -98,9 +98,11 @@ YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)
     // no cancellation: the row scatter is a precomputed constant)
     double q = 0.0;
     auto epilogue = [&](const int nb, const double c0, const double c1) {
-        const int col = nb + 2 * t;
-        const double e0 = c0 + L.bd[col], e1 = c1 + L.bd[col + 1];      // A @ theta + b - mean(data)
-        q = fma(L.nw[col + 1] * e1, e1, fma(L.nw[col] * e0, e0, q));
+        const int col = nb + 2 * t;                                      // even: one 16-byte load per operand pair
+        const double2 bd = *reinterpret_cast<const double2 *>(L.bd + col);
+        const double2 nw = *reinterpret_cast<const double2 *>(L.nw + col);
+        const double e0 = c0 + bd.x, e1 = c1 + bd.y;                    // A @ theta + b - mean(data)
+        q = fma(nw.y * e1, e1, fma(nw.x * e0, e0, q));
     };
     // four independent accumulator tiles per pass: a chain of dependent DMMAs alone cannot fill the pipe
     int nb = 0;
