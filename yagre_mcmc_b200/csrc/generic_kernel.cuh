@@ -183,7 +183,7 @@ constexpr int WS_THREADS = 64;             // 1 consumer warp + 1 producer warp 
 constexpr int64_t WS_MAX_CHAINS = 32768;   // beyond this the plain kernel has enough warps per sub-partition
 
 template <int D, int DD, bool TWO_LEVEL, bool WS>
-__global__ void __launch_bounds__(256) generic_mh_kernel(const RunArgs a)
+__global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ws_ring = nullptr;
