@@ -239,11 +239,11 @@ def run_gpu_arm(args):
                              "tflops": rk4_rate * 40e-12, "frac": rk4_rate * 40e-12 / peak,
                              "slot_frac": rk4_rate * 46e-12 / peak},
                 "rk4_loop": {"steps_per_s": rk4_rate, "bare_loop_steps_per_s": loop_rate, "frac": rk4_rate / loop_rate,
-                             "note": "whole MH kernel against nothing but lv_integrate at 1024 threads per SM"},
+                             "note": "whole MH kernel against nothing but lv_integrate (1024 threads per SM; the bare loop is flat from 512 up)"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full capture of this
-                # command, profiles/r01_lv_mh_kernel_ncu_full.csv): 5.85 MB + 0.79 MB; the algorithmic state
+                # command, profiles/r01_lv_mh_kernel_ncu_full.csv): 6.0 MB + 0.05 MB; the algorithmic state
                 # traffic is 96 B per chain per launch = 6.3 MB at 65,536 chains (written state stays in L2)
-                "traffic": 6.64e6 if (args.chains == CHAINS_PER_GPU) else None,
+                "traffic": 6.06e6 if (args.chains == CHAINS_PER_GPU) else None,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_lv_mh_kernel_ncu_full.csv",
                 "algorithmic_bytes_per_launch": 96.0 * args.chains,
                 "kernel": "lv_mh_kernel<true>", "launch_ms": total_ms_max / args.steps,

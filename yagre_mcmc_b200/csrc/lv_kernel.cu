@@ -513,15 +513,17 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
     const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
     const bool two = e->cfg.n_levels == 2;
     const int nd_max = std::max(hp->lvl[0].n_data, two ? hp->lvl[1].n_data : 0);
-    // Default geometry (profiles/r01_lv_tuning.md): ONE persistent CTA per SM with up to 1024
-    // threads.  Several smaller CTAs per SM finish at very different times because the FP64
-    // issue arbiter is not fair between CTAs, which leaves SMs half empty towards the end.
+    // Default geometry (profiles/r01_lv_tuning.md): ONE persistent CTA per SM with up to 768 threads
+    // (6 warps per sub-partition saturate the FP64 pipe, and 768 threads leave 80 registers per thread:
+    // fewer spills in the owners' phases than the 64 of 1024 threads, +2 %).  Several smaller CTAs per SM
+    // finish at very different times because the FP64 issue arbiter is not fair between CTAs, which
+    // leaves SMs half empty towards the end.
     int bps = e->cfg.blocks_per_sm > 0 ? e->cfg.blocks_per_sm : 1;
     int threads = e->cfg.threads_per_block;
     if (threads <= 0) {
         const int64_t ctas = std::min<int64_t>((int64_t)e->sm_count * bps, a.n_chains);
         const int64_t items = ((a.n_chains + ctas - 1) / ctas) * nd_max;
-        threads = (int)std::min<int64_t>(1024 / bps, std::max<int64_t>(128, (items + 31) / 32 * 32));
+        threads = (int)std::min<int64_t>((bps == 1 ? 768 : 1024) / bps, std::max<int64_t>(128, (items + 31) / 32 * 32));
     }
     if (threads % 32 || threads > 1024) {
         yg_set_error("threads_per_block must be a multiple of 32 and <= 1024 (got %d)", threads);
@@ -546,9 +548,10 @@ int yg_launch_lv(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
         args.lv_h[l] = hp->lvl[l].T / (double)hp->lvl[l].rk4_steps;
         args.lv_k[l] = lv_step_consts(hp->lvl[l].alpha, hp->lvl[l].gamma, args.lv_h[l]);
     }
-    // <= 512 threads: up to 128 registers per thread (no spills in the owners' phases)
+    // register budget follows the thread count: 128 (<= 512 threads), 80 (<= 768), 64 (<= 1024)
     auto kern = threads <= 512 ? (two ? lv_mh_kernel<true, 512> : lv_mh_kernel<false, 512>)
-                               : (two ? lv_mh_kernel<true, 1024> : lv_mh_kernel<false, 1024>);
+                : threads <= 768 ? (two ? lv_mh_kernel<true, 768> : lv_mh_kernel<false, 768>)
+                                 : (two ? lv_mh_kernel<true, 1024> : lv_mh_kernel<false, 1024>);
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int seg_len = e->cfg.rk4_segment > 0 ? e->cfg.rk4_segment : 128;
     kern<<<grid, threads, smem, st>>>(args, cmax, seg_len);
