@@ -21,10 +21,9 @@
 //     integrations over ALL its threads, so a chain whose coarse sub-chain did not
 //     move (no fine evaluation, mlda.py / metropolisHastings.py:60-61) costs
 //     nothing in the fine phase -- block-level compaction instead of lane masks;
-//   * ODE state and the four scaled rate constants live in registers, chain state
-//     lives in shared memory between phases so the integration loop stays small
-//     enough for 1024 resident threads/SM; several CTAs per SM sit in different
-//     phases, which hides the owners' phases and the tails of the item loops;
+//   * ODE state and the chain's six scaled rate constants live in registers, chain
+//     state lives in shared memory between phases so the integration loop stays
+//     small; one CTA of 768 threads per SM (80 registers per thread) by default;
 //   * the problem blob (design points, observations, precisions) is staged once
 //     per CTA into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier);
 //   * proposal noise does not depend on the chain state (counter-based Philox), so
