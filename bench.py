@@ -328,11 +328,23 @@ def run_gpu_arm(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ss)
+        # pooled diagnostics of the same run over ALL chains of ALL ranks (the path's only collectives, outside the
+        # timed sampling region): R-hat and moments from the all-reduced sufficient statistics, split-R-hat from
+        # per-chain half moments (yg_pooled_stats / yg_split_moments -> parallel.py)
+        from yagre_mcmc_b200.parallel import pooled_diagnostics, split_rhat
+        pd_ = pooled_diagnostics(ens)
+        srh = split_rhat(out["samples"][args.ess_burnin:])
+        diagnostics = {"n_chains": pd_["n_chains"], "pooled_mean": [float(x) for x in pd_["mean"]],
+                       "pooled_variance": [float(x) for x in np.diag(pd_["covariance"])],
+                       "acceptance_rate": float(pd_["acceptance_rate"]), "rhat": [float(x) for x in pd_["rhat"]],
+                       "split_rhat": [float(x) for x in srh],
+                       "collective": "all_reduce(sum) of %d doubles (NCCL)" % (3 + 2 * 2 + 2 * 4) if world > 1 else "single rank"}
         ess = {"ess_per_s": float(ss[0].item()) / (float(tt[0].item()) * 1e-3), "ensemble_ess": float(ss[0].item()),
                "mean_iat_max": float(ss[1].item()) / (nc * n_gpus), "chain_length": args.ess_steps,
                "burn_in": args.ess_burnin, "sampling_ms": float(tt[0].item()), "iat_kernel_ms": float(tt[1].item()),
                "definition": "per chain (N - burnIn) // IAT_max (example_inference_lotkaVolterra_twoLevel.py:117-118,132), "
-                             "summed over chains / sampling wall time (burn-in included)"}
+                             "summed over chains / sampling wall time (burn-in included)",
+               "diagnostics": diagnostics}
         del out
 
     # ---- the other BASELINE.json configs, briefly (rank 0, N = 1): parity-tested elsewhere, timed here ----
