@@ -112,6 +112,30 @@ def test_rk4_forward_matches_the_reference_solver():
         np.testing.assert_allclose(a["rk4_1024"][i], a["ref_forward"][i], rtol=2e-5)
 
 
+def test_stage_point_rk4_step_is_the_textbook_step():
+    """The device integrates with the 20-instruction "stage-point" form of the RK4 step (csrc/lv_model.cuh):
+    x' = k1/6 + (2/3) x3 + x4 (1/3 + (ha - hb y4)/6) with x2 = x + k1/2, x3 = x + k2/2, x4 = x + k3.  Restated
+    here in numpy (same operation order as the kernel, FMAs unfused) against the textbook form the oracle uses:
+    an algebraic identity, so the two agree to rounding after 512 steps."""
+    import bench_problems as bp
+    _, a = load("lv_forward")
+    design, (alpha, gamma, T) = a["design"], a["lv"]
+    for th in a["thetas"]:
+        for N in (64, 512):
+            h = T / N
+            hb, hd, ha, hg = h * np.exp(th[0]), h * np.exp(th[1]), h * alpha, h * gamma
+            x, y = design[:, 0].copy(), design[:, 1].copy()
+            for _ in range(N):
+                tx, ty = x * (-hb / 6 * y + ha / 6), y * (hd / 6 * x - hg / 6)
+                x2, y2 = 3.0 * tx + x, 3.0 * ty + y
+                x3, y3 = x2 * (-hb / 2 * y2 + ha / 2) + x, y2 * (hd / 2 * x2 - hg / 2) + y
+                x4, y4 = x3 * (-hb * y3 + ha) + x, y3 * (hd * x3 - hg) + y
+                wx, wy = -hb / 6 * y4 + (ha / 6 + 1.0 / 3.0), hd / 6 * x4 + (1.0 / 3.0 - hg / 6)
+                x, y = x4 * wx + (2.0 / 3.0 * x3 + tx), y4 * wy + (2.0 / 3.0 * y3 + ty)
+            want = bp.lv_forward_numpy(th, design, alpha, gamma, T, N)
+            np.testing.assert_allclose(np.stack([x, y], axis=1), want, rtol=5e-13)
+
+
 def test_philox_known_answers():
     """Random123 kat_vectors for philox4x32-10."""
     assert cport.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
