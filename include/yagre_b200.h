@@ -19,7 +19,9 @@
  *                            SolverInterface plugins model/interface.py:7-67
  *                            (LV: test/testSetup.py:61-141, linear: exampleSetup.py:8-52,
  *                            Gaussian targets: test/testSetup.py:15-44)
- *   yg_set_state             initialState of MetropolisHastings.run  chain/metropolisHastings.py:103-110
+ *   yg_set_state / yg_seek   initialState of MetropolisHastings.run  chain/metropolisHastings.py:103-110; the
+ *                            stream position plays the role of numpy's global generator state
+ *                            (statistics/gaussian.py:2,63, chain/metropolisHastings.py:2,68)
  *   yg_run                   the loop of MetropolisHastings.run :112-120 with
  *                            MRWProposal mrw.py:27-38, PCNProposal pcn.py:23-35, _accept_reject :55-73,
  *                            MLDAProposal.generate_proposal mlda.py:100-110 and
@@ -65,7 +67,8 @@
 extern "C" {
 #endif
 
-#define YG_ABI_VERSION 3u
+#define YG_ABI_VERSION 4u
+#define YG_MAX_LEVELS 3         /* densities per problem: up to two surrogates + the target */
 #define YG_MAX_DIM 8           /* parameter dimension of the one-chain-per-thread kernels */
 #define YG_MAX_DATA_DIM 8
 /* YG_MODEL_LINEAR beyond those sizes runs on the FP64 tensor path (DMMA GEMM, linear_dmma_kernel.cu):
@@ -108,14 +111,22 @@ typedef struct yg_level {
     const double *design;       /* [n_data, 2] */
     double alpha, gamma, T;
     int32_t rk4_steps;
-    int32_t _pad;
+    /* TemperedUnnormalisedPosterior (chain/target.py:25-43): tempering * logL + logprior when tempered != 0
+     * (regression levels of the one-chain-per-thread and LV kernels; tempering in [0, 1]) */
+    int32_t tempered;
+    double tempering;
 } yg_level;
 
 typedef enum yg_proposal { YG_PROPOSAL_MRW = 0, YG_PROPOSAL_PCN = 1 } yg_proposal;
 
 typedef struct yg_problem {
     const double *prop_L;       /* [d,d] lower-triangular proposal factor, p = s + L z */
-    yg_level level[2];          /* level[n_levels-1] is the target, level[0] the surrogate */
+    /* level[n_levels-1] is the target.  n_levels == 2: level[0] is the surrogate of two-level delayed
+     * acceptance.  n_levels == 3 is MLDA with TWO surrogates exactly as the reference runs it
+     * (chain/method/mlda.py:12-43,60-71,112-117): the proposal is the end point of an MRW sub-chain on
+     * level[0] of sub_chain_length = subChainLengths[1] steps (subChainLengths[0] is ignored there), and the
+     * screen is min(1, exp(pi_2(p) + pi_1(s) - pi_1(p) - pi_2(s))) with the FINEST surrogate level[1]. */
+    yg_level level[YG_MAX_LEVELS];
     /* YG_PROPOSAL_PCN (chain/method/pcn.py:9-57, single level): prop_L is the factor of the PRIOR
      * covariance, p = sqrt(1 - 2h) s + sqrt(2h) (pcn_mean + L z); the target is the likelihood
      * alone, i.e. the caller passes a zero prior_prec for the level. */
@@ -133,12 +144,17 @@ typedef struct yg_config {
     uint64_t seed;
     int32_t model;              /* yg_model */
     int32_t dim;                /* parameter dimension, 1..YG_MAX_DIM (LV: 2) */
-    int32_t n_levels;           /* 1 = MRW, 2 = two-level delayed acceptance (MLDA with one surrogate) */
-    int32_t sub_chain_length;   /* J (n_levels == 2), else ignored */
+    int32_t n_levels;           /* 1 = MRW, 2 = two-level delayed acceptance (MLDA with one surrogate),
+                                   3 = MLDA with two surrogates (see yg_problem.level) */
+    int32_t sub_chain_length;   /* J (n_levels >= 2), else ignored */
     int32_t eq_mode;            /* yg_eq_mode: ParameterVector (exact) / ScalarParameter (isclose) */
-    int32_t adaptive;           /* 0 = fixed proposal, 1 = per-chain adaptive Metropolis (n_levels == 1) */
-    int64_t am_idle_steps;      /* steps before moments are collected */
-    int64_t am_collection_steps;/* collected steps before the proposal switches */
+    /* 1 = per-chain adaptive Metropolis: AdaptiveMRWProposal.set_state -> update() (chain/adaptive.py:55-60)
+     * before EVERY proposal of the MRW chain it drives, with that chain's current state -- the chain state for
+     * one level, the sub-chain state for the coarse MRW of delayed acceptance (then idle / collection count
+     * coarse proposals).  All models of the one-chain-per-thread and LV kernels, dim >= 2. */
+    int32_t adaptive;
+    int64_t am_idle_steps;      /* updates before moments are collected */
+    int64_t am_collection_steps;/* collected states before the proposal switches */
     int32_t am_refresh;         /* recompute the Cholesky factor every R steps (>= 1) */
     int32_t _pad0;
     double am_eps;              /* regularisation: C = s (Cov + eps I) */
@@ -171,6 +187,11 @@ typedef struct yg_outputs {
     double *logpost_dev;        /* [n_steps/thin, n_levels, n_chains] log-posterior of the stored state, or NULL */
 } yg_outputs;
 
+/* yg_set_state flags.  The reference keeps diagnostics until clear() (chain/metropolisHastings.py:122-125) and
+ * the state of an adaptive proposal / error model for the life of the object; a second run() only restarts the chain. */
+#define YG_KEEP_DIAGNOSTICS 1   /* keep accept counters, Welford moments and the evaluation counters */
+#define YG_KEEP_ADAPTATION  2   /* keep adaptive-Metropolis moments / factors and the adaptive error model */
+
 /* Per-chain state, for diagnostics and bit-exact resume.  Any pointer may be NULL. */
 typedef struct yg_state {
     double *theta_dev;          /* [d, n_chains] */
@@ -195,9 +216,13 @@ int yg_create(const yg_config *cfg, yg_ensemble **out);
 int yg_destroy(yg_ensemble *e);
 int yg_set_problem(yg_ensemble *e, const yg_problem *pb);
 
-/* theta0_dev[d, n_chains]; evaluates the log-posterior(s) of the initial state
- * and resets counters, Welford and the step index. */
-int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stream);
+/* theta0_dev[d, n_chains]; evaluates the log-posterior(s) of the initial state and resets the diagnostics
+ * and the adaptation state unless `flags` keeps them.  The Philox stream position (step index) is NOT
+ * touched: like the reference's numpy generator it keeps advancing across runs, so two runs from the same
+ * state see different noise.  yg_seek repositions it explicitly. */
+int yg_set_state(yg_ensemble *e, const double *theta0_dev, int32_t flags, void *stream);
+/* Sets the Philox stream position: the next yg_run draws the noise of steps step_index, step_index + 1, ... */
+int yg_seek(yg_ensemble *e, int64_t step_index);
 
 /* Replaces the proposal factor L (host, [d, d] row-major, lower triangular, positive diagonal) for the
  * following yg_run calls: every chain of an adaptive ensemble restarts from it, a non-adaptive ensemble
@@ -211,17 +236,22 @@ int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin,
            const yg_outputs *out, const yg_noise *noise, void *stream);
 
 int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream);
-int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n, void *stream);
+/* am_steps: transitions since the adaptation state was reset (index base of the adaptive-Metropolis updates). */
+int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n, int64_t am_steps,
+                  void *stream);
 
-/* out_host[6] = {step index, transitions done (all chains), accepted, coarse forward evals,
- * fine (target-level) forward evals, welford n}.  Synchronises `stream`. */
+/* out_host[8] = {step index, transitions done (all chains), accepted, level-0 forward evals,
+ * target-level forward evals, welford n, am_steps, level-1 forward evals of a three-level hierarchy}.
+ * Synchronises `stream`. */
 int yg_get_counters(yg_ensemble *e, int64_t *out_host, void *stream);
 
 /* log-posterior of theta_dev[d, n] at `level` -> out_dev[n] (same kernels' device functions). */
 int yg_logpost(yg_ensemble *e, int32_t level, const double *theta_dev, int64_t n, double *out_dev, void *stream);
 
 /* samples_dev[n_samples, d, n_chains] -> iat_dev[n_chains] (max over coordinates, Sokal window c),
- * ess_dev[n_chains] = n_samples / max(iat,1) (integer division), either may be NULL.
+ * ess_dev[n_chains] = n_samples / max(iat,1) (integer division), either may be NULL.  A chain whose stored
+ * series is constant or non-finite (no autocorrelation function; the reference fails on it) reports
+ * iat = n_samples and ess = 0.
  * method: 0 = 'mean', 1 = 'max'.  Series of more than 25,600 samples use a stream-ordered scratch
  * allocation (cudaMallocAsync / cudaFreeAsync on `stream`; still no host synchronisation). */
 int yg_iat_ess(const double *samples_dev, int64_t n_samples, int32_t d, int64_t n_chains,

@@ -22,12 +22,12 @@ class YoLevel(C.Structure):
                 ("data", _dp), ("noise_prec", _dp), ("prior_mean", _dp), ("prior_prec", _dp),
                 ("G", _dp), ("b", _dp), ("design", _dp),
                 ("alpha", C.c_double), ("gamma", C.c_double), ("T", C.c_double),
-                ("rk4_steps", C.c_int32), ("_pad", C.c_int32)]
+                ("rk4_steps", C.c_int32), ("tempered", C.c_int32), ("tempering", C.c_double)]
 
 
 class YoProblem(C.Structure):
     _fields_ = [("model", C.c_int32), ("dim", C.c_int32), ("n_levels", C.c_int32), ("J", C.c_int32),
-                ("eq_mode", C.c_int32), ("_pad", C.c_int32), ("prop_L", _dp), ("level", YoLevel * 2),
+                ("eq_mode", C.c_int32), ("_pad", C.c_int32), ("prop_L", _dp), ("level", YoLevel * 3),
                 ("adaptive", C.c_int32), ("am_refresh", C.c_int32), ("am_idle", C.c_int64),
                 ("am_collect", C.c_int64), ("am_eps", C.c_double), ("am_scale", C.c_double),
                 ("pcn", C.c_int32), ("_pad2", C.c_int32), ("pcn_a", C.c_double), ("pcn_b", C.c_double),
@@ -70,6 +70,7 @@ class Problem:
 
     def __init__(self, meta, arrays, adaptive=None):
         self.meta = dict(meta)
+        adaptive = adaptive or meta.get('am')
         self.keep = {}
         pb = YoProblem()
         pb.model = MODEL[meta['model']]
@@ -84,7 +85,7 @@ class Problem:
             pb.am_collect = int(adaptive.get('collection', 100))
             pb.am_refresh = int(adaptive.get('refresh', 1))
             pb.am_eps = float(adaptive.get('eps', 1e-4))
-            sc = float(adaptive.get('scale', 0.0))
+            sc = float(adaptive.get('scale') or 0.0)
             pb.am_scale = sc if sc > 0 else 2.4 * 2.4 / int(meta['dim'])
 
         if meta.get('proposal', 'mrw') == 'pcn':
@@ -115,6 +116,8 @@ class Problem:
             if pre + "lv" in arrays:
                 a = np.asarray(arrays[pre + "lv"], dtype=np.float64)
                 lv.alpha, lv.gamma, lv.T, lv.rk4_steps = float(a[0]), float(a[1]), float(a[2]), int(a[3])
+            if pre + "tempering" in arrays:
+                lv.tempered, lv.tempering = 1, float(np.asarray(arrays[pre + "tempering"]).reshape(-1)[0])
         self.pb = pb
         self.dim, self.J, self.n_levels = pb.dim, pb.J, pb.n_levels
 
@@ -129,18 +132,23 @@ def run_injected(problem, theta0, z, u_c, u_f, n_threads=0):
     acc = np.empty((nc, ns), dtype=np.uint8)
     lp0 = np.empty((nc, ns + 1))
     lp1 = np.full((nc, ns + 1), np.nan)
+    lp2 = np.full((nc, ns + 1), np.nan)
     wm = np.empty((nc, d))
     wv = np.empty((nc, d))
-    ev = np.zeros(2, dtype=np.int64)
+    ev = np.zeros(3, dtype=np.int64)
     dd = int(problem.pb.level[0].data_dim)
     aem = np.zeros((nc, 2 + 2 * max(dd, 1)))
+    am = np.zeros((nc, d + 2 * d * d))
     rc = lib().yo_run_injected(C.byref(problem.pb), C.c_int64(nc), C.c_int64(ns),
                                _ptr(theta0), _ptr(z), _ptr(u_c), _ptr(u_f), _ptr(traj),
-                               acc.ctypes.data_as(C.c_void_p), _ptr(lp0), _ptr(lp1), _ptr(wm), _ptr(wv),
-                               ev.ctypes.data_as(C.c_void_p), C.c_int(n_threads), _ptr(aem))
+                               acc.ctypes.data_as(C.c_void_p), _ptr(lp0), _ptr(lp1), _ptr(lp2), _ptr(wm), _ptr(wv),
+                               ev.ctypes.data_as(C.c_void_p), C.c_int(n_threads), _ptr(aem), _ptr(am))
     assert rc == 0
-    out = dict(traj=traj, accepted=acc, logpost_L0=lp0, logpost_L1=lp1,
+    out = dict(traj=traj, accepted=acc, logpost_L0=lp0, logpost_L1=lp1, logpost_L2=lp2,
                welford_mean=wm, welford_var=wv, n_evals=ev)
+    if problem.pb.adaptive:
+        out.update(am_mean=am[:, :d].copy(), am_m2=am[:, d:d + d * d].reshape(nc, d, d).copy(),
+                   am_L=am[:, d + d * d:].reshape(nc, d, d).copy())
     if problem.pb.aem:
         out.update(aem_n=aem[:, 0].astype(np.int64), aem_model_evals=aem[:, 1].astype(np.int64),
                    aem_mean=aem[:, 2:2 + dd], aem_var=aem[:, 2 + dd:2 + 2 * dd])

@@ -529,6 +529,256 @@ def cases_aem():
     case_aem("aem_linear_noheuristic", 12, False, 400, 1501)
 
 
+
+# --------------------------------------------------------------------------
+# adaptive Metropolis through the reference's live interface (chain/adaptive.py:8-64):
+# the unmodified AdaptiveMRWProposal + MetropolisHastings.run drive OUR concrete
+# AdaptiveCovarianceMatrix (ref_harness.HaarioAdaptiveCovariance)
+# --------------------------------------------------------------------------
+
+def _am_finish(name, meta, arrays, covs, am):
+    arrays.update(am_mean=np.array([c.mean for c in covs]), am_m2=np.array([c.M2 for c in covs]),
+                  am_L=np.array([c.chol_factor() for c in covs]), am_t=np.array([c.t for c in covs]),
+                  am_refreshes=np.array([c.nRefresh for c in covs]))
+    meta['am'] = am
+    for c, cv in enumerate(covs):
+        print(f"    {name} chain {c}: {cv.t} updates, {cv.nRefresh} Cholesky refreshes")
+    save(name, meta, arrays)
+
+
+def case_am_gauss2d(name, am, seed, nSteps=300):
+    nChains = 3
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, 2, zero_at=[(2, 11, 0)])
+    mean, cov = np.array([1., 1.5]), np.array([[3.2, -0.4], [-0.4, 0.2]])       # test/test_adaptive.py:16-19
+    tgt = rh.GaussianTargetDensity2d(rh.ParameterVector(mean), cov)
+    traj, acc, lp, covs = [], [], [], []
+    for c in range(nChains):
+        inj = rh.NoiseInjector(z[c], None, u_f[c])
+        ac = rh.HaarioAdaptiveCovariance(rh.IIDCovarianceMatrix(2, 0.25), am['idle'], am['collection'], am['eps'],
+                                         am.get('scale'), am.get('refresh', 1))
+        mcmc = rh.AdaptiveMetropolis(tgt, ac, rh.FullDiagnostics())
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.array([0., -1.])), nSteps, inj, False)
+        traj.append(t); acc.append(a); covs.append(ac)
+        lp.append(logpost_along(tgt, rh.ParameterVector, t))
+    m, P, lc = gauss2d_level_arrays(mean, cov)
+    meta = dict(model='gauss', dim=2, levels=1, J=1, eq='exact',
+                note='adaptive Metropolis: reference AdaptiveMRWProposal (chain/adaptive.py:37-64) + '
+                     'MetropolisHastings.run + our HaarioAdaptiveCovariance; target of test/test_adaptive.py:16-21')
+    _am_finish(name, meta, dict(prop_L=lower_proposal('iid', 0.25, 2), L0_g_mean=m, L0_g_prec=P, L0_g_logconst=lc,
+                                theta0=np.tile([0., -1.], (nChains, 1)), z=z, u_c=u_c, u_f=u_f, traj=traj,
+                                accepted=acc, logpost_L0=lp), covs, am)
+
+
+def case_am_lv(name, twoLevel, am, seed, nSteps=120, J=3):
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = lv_problem()
+    nChains = 3
+    J = J if twoLevel else 1
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 4, None), (1, 9, 1)] if twoLevel else [(0, 6, 0)])
+    theta0 = p['truth'] + 0.05 * Generator(Philox(7)).standard_normal((3, 2))
+    propVar = 0.1 if twoLevel else 0.15
+    traj, acc, lpc, lpf, covs = [], [], [], [], []
+    for c in range(nChains):
+        likC, likF, prior = lv_models(p)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        ac = rh.HaarioAdaptiveCovariance(rh.IIDCovarianceMatrix(2, propVar), am['idle'], am['collection'], am['eps'],
+                                         am.get('scale'), am.get('refresh', 1))
+        if twoLevel:
+            b = rh.MLDABuilder()
+            b.bayesModel = rh.BayesianRegressionModelHierarchy(
+                rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+            b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, propVar)
+            b.subChainLengths = [J]
+            mcmc = rh.make_surrogate_adaptive(rh.quiet(b.build_method), ac)
+        else:
+            mcmc = rh.AdaptiveMetropolis(UnnormalisedPosterior(likF, prior), ac, rh.FullDiagnostics())
+        init = rh.LotkaVolterraParameter.from_coefficient(theta0[c].copy())
+        t, a = rh.run_reference_chain(mcmc, init, nSteps, inj, twoLevel)
+        traj.append(t); acc.append(a); covs.append(ac)
+        lpf.append(logpost_along(UnnormalisedPosterior(likF, prior), rh.LotkaVolterraParameter, t))
+        if twoLevel:
+            lpc.append(logpost_along(UnnormalisedPosterior(likC, prior), rh.LotkaVolterraParameter, t))
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('iid', propVar, 2), theta0=theta0, z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc)
+    if twoLevel:
+        arrays.update(lv_level_arrays(p, p['Nc'], 'L0_')); arrays.update(lv_level_arrays(p, p['Nf'], 'L1_'))
+        arrays.update(logpost_L0=lpc, logpost_L1=lpf)
+    else:
+        arrays.update(lv_level_arrays(p, p['Nf'], 'L0_'))
+        arrays.update(logpost_L0=lpf)
+    meta = dict(model='lv', dim=2, levels=2 if twoLevel else 1, J=J, eq='exact',
+                note=('C5' if twoLevel else 'C4') + ' with an adaptive (coarse) proposal: reference AdaptiveMRWProposal '
+                     '(chain/adaptive.py:37-64) ' + ('as the proposal method of the MLDA surrogate MRW, update() before '
+                     'every coarse proposal' if twoLevel else '+ MetropolisHastings.run'))
+    _am_finish(name, meta, arrays, covs, am)
+
+
+def case_am_mlda_linear(name, am, seed, nSteps=300, J=5):
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = linear_problem()
+    nChains = 3
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 4, None), (1, 8, 1)])
+    traj, acc, lpc, lpf, covs = [], [], [], [], []
+    for c in range(nChains):
+        likC, likF, prior = linear_models(p)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        ac = rh.HaarioAdaptiveCovariance(rh.IIDCovarianceMatrix(2, p['propVar']), am['idle'], am['collection'],
+                                         am['eps'], am.get('scale'), am.get('refresh', 1))
+        b = rh.MLDABuilder()
+        b.bayesModel = rh.BayesianRegressionModelHierarchy(rh.Hierarchy([likC, likF]), rh.SharedComponent(prior, 2))
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+        b.subChainLengths = [J]
+        mcmc = rh.make_surrogate_adaptive(rh.quiet(b.build_method), ac)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.zeros(2)), nSteps, inj, True)
+        traj.append(t); acc.append(a); covs.append(ac)
+        lpf.append(logpost_along(UnnormalisedPosterior(likF, prior), rh.ParameterVector, t))
+        lpc.append(logpost_along(UnnormalisedPosterior(likC, prior), rh.ParameterVector, t))
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], 2), theta0=np.zeros((nChains, 2)), z=z, u_c=u_c, u_f=u_f,
+                  traj=traj, accepted=acc, logpost_L0=lpc, logpost_L1=lpf)
+    arrays.update(linear_level_arrays(p, 'c', 'L0_')); arrays.update(linear_level_arrays(p, 'f', 'L1_'))
+    meta = dict(model='linear', dim=2, levels=2, J=J, eq='exact',
+                note='C3 with an adaptive coarse proposal (AdaptiveMRWProposal on the MLDA surrogate MRW)')
+    _am_finish(name, meta, arrays, covs, am)
+
+
+def cases_am():
+    case_am_gauss2d("am_gauss2d", dict(idle=20, collection=40, eps=1e-4, refresh=1), 1601)
+    case_am_gauss2d("am_gauss2d_refresh7", dict(idle=0, collection=25, eps=1e-3, refresh=7, scale=1.7), 1602)
+    case_am_lv("am_lv", False, dict(idle=10, collection=30, eps=1e-6, refresh=1), 1603)
+    case_am_lv("am_mlda_lv", True, dict(idle=15, collection=60, eps=1e-6, refresh=1), 1604)
+    case_am_mlda_linear("am_mlda_linear", dict(idle=10, collection=100, eps=1e-4, refresh=3), 1605)
+
+
+# --------------------------------------------------------------------------
+# MLDA with TWO surrogates, as the reference actually runs it (chain/method/mlda.py:12-43,60-71,112-117):
+# the proposal is the end point of subChainLengths[1] MRW steps on the BASE surrogate (subChainLengths[0]
+# is ignored) and the screen uses the FINEST surrogate.  Constants: test/test_mlda.py:14-60 and
+# example_mcmc_2d_hierarchical.py:10-44.
+# --------------------------------------------------------------------------
+
+def case_mlda3_gauss2d(name, baseCovScale, fineCovScale, nStepsList, seed, nSteps=250, distinctLengths=False):
+    nChains = 3
+    J = nStepsList[1]
+    rng = Generator(Philox(seed))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 3, None), (1, 14, 2), (2, 30, None)])
+    baseMean, fineMean = TGT_MEAN + np.array([-0.05, 0.01]), TGT_MEAN + np.array([0.0, -0.01])
+    baseCov = baseCovScale * np.array([[2.8, -0.1], [-0.1, 1.7]])
+    fineCov = fineCovScale * np.array([[2.4, -0.3], [-0.3, 1.1]])
+    tgt = rh.GaussianTargetDensity2d(rh.ParameterVector(TGT_MEAN), TGT_COV)
+    base = rh.GaussianTargetDensity2d(rh.ParameterVector(baseMean), baseCov)
+    fine = rh.GaussianTargetDensity2d(rh.ParameterVector(fineMean), fineCov)
+    traj, acc, lp0, lp1, lp2, order = [], [], [], [], [], []
+    for c in range(nChains):
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        b = rh.MLDABuilder()
+        b.explicitTarget = tgt
+        b.surrogateTargets = [base, fine]
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, 1.)
+        b.subChainLengths = list(nStepsList)
+        mcmc = rh.quiet(b.build_method)
+        assert mcmc.nSurrogates == 2
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.array([-8., -7.])), nSteps, inj, True)
+        traj.append(t); acc.append(a)
+        lp0.append(logpost_along(base, rh.ParameterVector, t))
+        lp1.append(logpost_along(fine, rh.ParameterVector, t))
+        lp2.append(logpost_along(tgt, rh.ParameterVector, t))
+        order.append(''.join(inj.log))
+        print(f"    {name} chain {c}: acceptance {a.mean():.3f}")
+    m0, P0, c0 = gauss2d_level_arrays(baseMean, baseCov)
+    m1, P1, c1 = gauss2d_level_arrays(fineMean, fineCov)
+    m2, P2, c2 = gauss2d_level_arrays(TGT_MEAN, TGT_COV)
+    meta = dict(model='gauss', dim=2, levels=3, J=J, eq='exact', rng_order=order, subChainLengths=list(nStepsList),
+                note='MLDA with two surrogates (mlda.py:12-43,60-71,112-117): test/test_mlda.py:14-60 / '
+                     'example_mcmc_2d_hierarchical.py:10-44')
+    save(name, meta, dict(prop_L=lower_proposal('iid', 1., 2),
+                          L0_g_mean=m0, L0_g_prec=P0, L0_g_logconst=c0, L1_g_mean=m1, L1_g_prec=P1, L1_g_logconst=c1,
+                          L2_g_mean=m2, L2_g_prec=P2, L2_g_logconst=c2,
+                          theta0=np.tile([-8., -7.], (nChains, 1)), z=z, u_c=u_c, u_f=u_f,
+                          traj=traj, accepted=acc, logpost_L0=lp0, logpost_L1=lp1, logpost_L2=lp2))
+
+
+def case_mlda3_linear():
+    """Three linear models through the Bayesian-model hierarchy (BayesianRegressionModelHierarchy of size 3)."""
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = linear_problem()
+    G_m = p['G_f'] + 0.3 * np.array([[-0.6, -0.2], [0.4, 1.1]])
+    b_m = 0.3 * p['b_c']
+    nChains, nSteps, J = 3, 250, 4
+    rng = Generator(Philox(1707))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 4, None), (1, 8, 1)])
+    traj, acc, lps = [], [], [[], [], []]
+    for c in range(nChains):
+        data = rh.Data(p['data'])
+        noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(2, p['noiseVar']))
+        prior = rh.Gaussian(rh.ParameterVector(p['priorMean']), rh.IIDCovarianceMatrix(2, p['priorVar']))
+        liks = [rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(G, b)), noise)
+                for (G, b) in ((p['G_c'], p['b_c']), (G_m, b_m), (p['G_f'], p['b_f']))]
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        b = rh.MLDABuilder()
+        b.bayesModel = rh.BayesianRegressionModelHierarchy(rh.Hierarchy(liks), rh.SharedComponent(prior, 3))
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+        b.subChainLengths = [7, J]
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.zeros(2)), nSteps, inj, True)
+        traj.append(t); acc.append(a)
+        for l in range(3):
+            lps[l].append(logpost_along(UnnormalisedPosterior(liks[l], prior), rh.ParameterVector, t))
+        print(f"    mlda3_linear chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], 2), theta0=np.zeros((nChains, 2)), z=z, u_c=u_c, u_f=u_f,
+                  traj=traj, accepted=acc, logpost_L0=lps[0], logpost_L1=lps[1], logpost_L2=lps[2])
+    for l, (G, bb) in enumerate(((p['G_c'], p['b_c']), (G_m, b_m), (p['G_f'], p['b_f']))):
+        pre = f'L{l}_'
+        arrays.update({pre + 'data': p['data'], pre + 'noise_prec': diag_precision(p['noiseVar'], 2),
+                       pre + 'prior_mean': p['priorMean'], pre + 'prior_prec': diag_precision(p['priorVar'], 2),
+                       pre + 'G': G, pre + 'b': bb})
+    meta = dict(model='linear', dim=2, levels=3, J=J, eq='exact', subChainLengths=[7, J],
+                note='MLDA over a hierarchy of three linear Bayesian models (C3 constants + an intermediate model)')
+    save("mlda3_linear", meta, arrays)
+
+
+def case_mlda_linear_tempered():
+    """Two-level delayed acceptance whose surrogate is a TemperedUnnormalisedPosterior (chain/target.py:25-43:
+    tempering * logL + logprior) -- the working part of the reference's tempering machinery (tmlda.py itself
+    cannot be constructed: TemperedMLDA.__init__ calls MLDA.__init__ with two arguments missing)."""
+    from yagremcmc.chain.target import UnnormalisedPosterior, TemperedUnnormalisedPosterior
+    p = linear_problem()
+    nChains, nSteps, J, tempering = 3, 250, 5, 0.35
+    rng = Generator(Philox(1801))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, J, 2, zero_at=[(0, 4, None), (1, 8, 1)])
+    traj, acc, lpc, lpf = [], [], [], []
+    for c in range(nChains):
+        likC, likF, prior = linear_models(p)
+        sur, tgt = TemperedUnnormalisedPosterior(likC, prior, tempering), UnnormalisedPosterior(likF, prior)
+        inj = rh.NoiseInjector(z[c], u_c[c], u_f[c])
+        b = rh.MLDABuilder()
+        b.explicitTarget = tgt
+        b.surrogateTargets = [sur]
+        b.baseProposalCovariance = rh.IIDCovarianceMatrix(2, p['propVar'])
+        b.subChainLengths = [J]
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(np.zeros(2)), nSteps, inj, True)
+        traj.append(t); acc.append(a)
+        lpf.append(logpost_along(tgt, rh.ParameterVector, t))
+        lpc.append(logpost_along(sur, rh.ParameterVector, t))
+        print(f"    mlda_linear_tempered chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('iid', p['propVar'], 2), theta0=np.zeros((nChains, 2)), z=z, u_c=u_c, u_f=u_f,
+                  traj=traj, accepted=acc, logpost_L0=lpc, logpost_L1=lpf, L0_tempering=tempering)
+    arrays.update(linear_level_arrays(p, 'c', 'L0_')); arrays.update(linear_level_arrays(p, 'f', 'L1_'))
+    meta = dict(model='linear', dim=2, levels=2, J=J, eq='exact',
+                note='C3 with a tempered surrogate: TemperedUnnormalisedPosterior(likC, prior, 0.35), chain/target.py:25-43')
+    save("mlda_linear_tempered", meta, arrays)
+
+
+def cases_mlda3():
+    case_mlda3_gauss2d("mlda3_gauss2d", 3.0, 1.5, [6, 6], 1701)                 # test/test_mlda.py:14-60
+    case_mlda3_gauss2d("mlda3_gauss2d_hier", 4.0, 2.0, [9, 4], 1702)            # example_mcmc_2d_hierarchical.py ([4,4]);
+    case_mlda3_linear()                                                        # [9,4]: subChainLengths[0] is ignored
+    case_mlda_linear_tempered()
+
 # --------------------------------------------------------------------------
 # post-processing pins: IAT, Welford, dense covariance
 # --------------------------------------------------------------------------
@@ -676,6 +926,10 @@ if __name__ == "__main__":
         cases_pcn()
     if want('aem'):
         cases_aem()
+    if want('am'):
+        cases_am()
+    if want('mlda3'):
+        cases_mlda3()
     if want('lvforward'):
         case_lv_forward()
     if want('lvlong'):

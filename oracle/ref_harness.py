@@ -274,3 +274,90 @@ def covariance_from_spec(kind, value, dim):
     if kind == 'dense':
         return DenseCovarianceMatrix(np.asarray(value, dtype=np.float64))
     raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------
+# adaptive Metropolis through the reference's LIVE interface
+# --------------------------------------------------------------------------
+from yagremcmc.chain.adaptive import AdaptiveCovarianceMatrix, AdaptiveMRWProposal   # noqa: E402
+from yagremcmc.chain.metropolisHastings import MetropolisHastings                   # noqa: E402
+
+
+class HaarioAdaptiveCovariance(AdaptiveCovarianceMatrix):
+    """OUR concrete AdaptiveCovarianceMatrix (the reference ships only the abstract class,
+    chain/adaptive.py:8-34, and a dead implementation, chain/method/deprecated/am.py).
+
+    What the reference pins: update() takes no argument, sees the chain through set_chain()
+    (adaptive.py:20-21) and is called by AdaptiveMRWProposal.set_state (adaptive.py:55-60), i.e.
+    by MetropolisHastings.run BEFORE every proposal (metropolisHastings.py:117), at which point
+    chain.trajectory[-1] is the current state; the covariance it returns is swapped into the MRW
+    proposal for the proposal drawn right after.
+
+    What is ours: with t the number of update() calls so far, for
+    t >= idle:  n = t - idle + 1;  delta = x - mean;  mean += delta / n;
+                M2 += outer(delta, x - mean)                    (Welford, full matrix)
+    and when n >= collection, n >= 2 and (n - collection) % refresh == 0:
+                C = scale * (0.5 (M2 + M2') / (n - 1) + eps I),  scale = 2.4^2 / d by default;
+    the proposal covariance becomes DenseCovarianceMatrix(C) (scipy Cholesky, covariance.py:69-86)
+    unless C is not positive definite, in which case the previous one is kept.
+    """
+
+    def __init__(self, initCov, idleSteps, collectionSteps, eps, scale=None, refresh=1):
+        super().__init__(initCov)
+        d = initCov.dimension
+        self.idle, self.collection, self.refresh = int(idleSteps), int(collectionSteps), int(refresh)
+        self.eps = float(eps)
+        self.scale = 2.4 * 2.4 / d if not scale else float(scale)
+        self.t = 0
+        self.mean = np.zeros(d)
+        self.M2 = np.zeros((d, d))
+        self.nRefresh = 0
+
+    def update(self):
+        x = np.asarray(self._chain.trajectory[-1], dtype=np.float64).reshape(-1)
+        t = self.t
+        self.t += 1
+        if t < self.idle:
+            return
+        n = t - self.idle + 1
+        delta = x - self.mean
+        self.mean = self.mean + delta / n
+        self.M2 = self.M2 + np.outer(delta, x - self.mean)
+        if n >= self.collection and n >= 2 and (n - self.collection) % self.refresh == 0:
+            cov = 0.5 * (self.M2 + self.M2.T) / (n - 1)
+            C = self.scale * (cov + self.eps * np.eye(x.size))
+            try:
+                self._cov = DenseCovarianceMatrix(C)
+                self.nRefresh += 1
+            except np.linalg.LinAlgError:
+                pass
+
+    def chol_factor(self):
+        """Current lower factor L (p = s + L z), in the lowered form of make_golden.lower_proposal."""
+        c = self._cov
+        if isinstance(c, DenseCovarianceMatrix):
+            return np.array(c.cholFactor_)
+        return np.diag(np.sqrt(np.reciprocal(c._precision)))
+
+
+class AdaptiveMetropolis(MetropolisHastings):
+    """Single-level adaptive MRW assembled from the reference's own parts: the unmodified
+    MetropolisHastings.run loop, the unmodified AdaptiveMRWProposal and the MRW acceptance rule
+    (chain/method/mrw.py:51-57)."""
+
+    def __init__(self, targetDensity, adaptiveCov, diagnostics):
+        super().__init__(targetDensity, AdaptiveMRWProposal(adaptiveCov), diagnostics)
+        adaptiveCov.set_chain(self._chain)
+
+    _acceptance_probability = MetropolisedRandomWalk._acceptance_probability
+
+
+def make_surrogate_adaptive(mlda, adaptiveCov):
+    """Two-level delayed acceptance with an adaptive coarse proposal: the MRW surrogate of an
+    unmodified MLDA object (mlda.py:58-62) gets the reference's AdaptiveMRWProposal as its proposal
+    method, bound to the surrogate's own chain.  update() is then called before every COARSE
+    proposal with the sub-chain's current state (metropolisHastings.py:117 of the surrogate's run)."""
+    sur = mlda.surrogate(0)
+    sur._proposalMethod = AdaptiveMRWProposal(adaptiveCov)
+    adaptiveCov.set_chain(sur.chain)
+    return mlda

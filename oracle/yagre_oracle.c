@@ -13,9 +13,11 @@
  * the RK4 forward model is our SolverInterface plugin because the reference
  * integrates with scipy.solve_ivp -- see oracle/ref_harness.py).  PINNED for
  * Welford, IAT and dense-covariance operators against postprocessing.npz.
- * UNPINNED for adaptive Metropolis (the reference has no working implementation,
- * chain/method/deprecated/am.py:152 raises) and for split-R-hat (absent from
- * the reference): those follow the recurrences written in DESIGN.md.
+ * PINNED for adaptive Metropolis against tests/golden/am_*.npz: the unmodified
+ * AdaptiveMRWProposal + MetropolisHastings.run (chain/adaptive.py:37-64) driving our concrete
+ * AdaptiveCovarianceMatrix (oracle/ref_harness.py; the reference ships only the abstract class,
+ * so the recurrence is ours, its call order / swap semantics / Cholesky are the reference's).
+ * UNPINNED for split-R-hat (absent from the reference; checked against numpy).
  *
  * Compile with -ffp-contract=off: the reference is numpy (unfused arithmetic).
  *
@@ -50,14 +52,18 @@ typedef struct yo_level {
     const double *design;      /* [n_data, 2]    testSetup.py:118-141 */
     double alpha, gamma, T;
     int32_t rk4_steps;
-    int32_t _pad;
+    int32_t tempered;          /* TemperedUnnormalisedPosterior (chain/target.py:25-43) */
+    double tempering;
 } yo_level;
 
 typedef struct yo_problem {
     int32_t model, dim, n_levels, J, eq_mode, _pad;
     const double *prop_L;      /* [d,d] lower triangular, p = s + L z (gaussian.py:61-66) */
-    yo_level level[2];         /* level[n_levels-1] is the target */
-    /* adaptive Metropolis (single level; recurrence of DESIGN.md, parity UNPINNED vs the reference) */
+    /* level[n_levels-1] is the target; n_levels == 3 is MLDA with two surrogates AS THE REFERENCE RUNS
+     * IT (mlda.py:12-43,60-71,112-117): MRW sub-chain of J = subChainLengths[1] steps on level[0],
+     * screen with the finest surrogate level[1] */
+    yo_level level[3];
+    /* adaptive Metropolis (am_update below; pinned by tests/golden/am_*.npz) */
     int32_t adaptive, am_refresh;
     int64_t am_idle, am_collect;
     double am_eps, am_scale;
@@ -185,6 +191,7 @@ double yo_logpost(const yo_problem *pb, int lvl, const double *theta, int64_t *n
     }
     double logL = -0.5 * np_pairwise_sum(q, nD);      /* likelihood.py:80 */
     free(q);
+    if (L->tempered) logL = L->tempering * logL;      /* target.py:40-43 */
     for (int i = 0; i < d; i++) x[i] = theta[i] - L->prior_mean[i];
     double lp = -0.5 * quad_form(L->prior_prec, x, d); /* gaussian.py:19-24 */
     return logL + lp;
@@ -332,9 +339,9 @@ static double get_uf(const noise_src *ns, int64_t n)
 
 typedef struct {
     double theta[YO_MAX_DIM];
-    double lp[2];                  /* log-posterior of theta per level */
+    double lp[3];                  /* log-posterior of theta per level */
     int64_t n_accept;
-    int64_t n_evals[2];
+    int64_t n_evals[3];
     int64_t w_n;                   /* Welford (estimation.py:36-53), fed the PRE-transition state */
     double w_mean[YO_MAX_DIM], w_m2[YO_MAX_DIM];
     /* adaptive Metropolis: full-matrix Welford of the states from step am_idle on + current factor */
@@ -351,18 +358,22 @@ typedef struct {
 
 int yo_cholesky(const double *C, int d, double *L);
 
-/* chain/adaptive.py:55-60: update() runs in set_state(), i.e. BEFORE each proposal, with the
- * current state.  Rule (ours): C = s (Cov + eps I) once am_collect states were collected. */
-static void am_update(const yo_problem *pb, chain_state *cs, int64_t t_idx)
+/* chain/adaptive.py:55-60: update() runs in AdaptiveMRWProposal.set_state(), i.e. BEFORE each
+ * proposal of the MRW chain it drives, with that chain's current state x: the chain state for a
+ * single level, the sub-chain state for the coarse MRW of two-level delayed acceptance.  t_idx =
+ * number of update() calls before this one.  The recurrence (Welford, C = s (Cov + eps I) once
+ * am_collect states were collected) is ours; its arithmetic is pinned to oracle/ref_harness.py
+ * HaarioAdaptiveCovariance driven by the unmodified reference (tests/golden/am_*.npz). */
+static void am_update(const yo_problem *pb, chain_state *cs, const double *x, int64_t t_idx)
 {
     const int d = pb->dim;
     if (t_idx < pb->am_idle) return;
     const int64_t n_am = t_idx - pb->am_idle + 1;
     double dl[YO_MAX_DIM], e[YO_MAX_DIM];
     for (int i = 0; i < d; i++) {
-        dl[i] = cs->theta[i] - cs->am_mean[i];
+        dl[i] = x[i] - cs->am_mean[i];
         cs->am_mean[i] += dl[i] / (double)n_am;
-        e[i] = cs->theta[i] - cs->am_mean[i];
+        e[i] = x[i] - cs->am_mean[i];
     }
     for (int i = 0; i < d; i++)
         for (int j = 0; j < d; j++) cs->am_m2[i * d + j] += dl[i] * e[j];
@@ -567,7 +578,7 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
     if (pb->aem) return chain_step_aem(pb, cs, ns, n);
     welford_update(cs, d);                               /* diagnostics.py:91-94 */
     if (pb->n_levels == 1) {
-        if (pb->adaptive) am_update(pb, cs, (int64_t)ns->step0 + n);
+        if (pb->adaptive) am_update(pb, cs, cs->theta, n);        /* n counts from chain_init, where the moments were reset */
         get_z(pb, ns, n, 0, z);
         propose(pb, cs->L, cs->theta, z, p);
         if (param_equal(pb, p, cs->theta)) return 0;     /* metropolisHastings.py:60-61 */
@@ -583,6 +594,7 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
     double s[YO_MAX_DIM], lpc_s = cs->lp[0];
     memcpy(s, cs->theta, sizeof(double) * d);
     for (int j = 0; j < pb->J; j++) {                    /* coarse MRW sub-chain */
+        if (pb->adaptive) am_update(pb, cs, s, n * pb->J + j);
         get_z(pb, ns, n, j, z);
         propose(pb, cs->L, s, z, p);
         if (param_equal(pb, p, s)) continue;
@@ -593,6 +605,20 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
         }
     }
     if (param_equal(pb, s, cs->theta)) return 0;         /* no fine evaluation, no uniform */
+    if (pb->n_levels == 3) {
+        /* two surrogates: MLDA._acceptance_probability (mlda.py:146-154) with _finestTarget = level 1,
+         * while the sub-chain above ran on level 0 (SurrogateTransition.generate_proposal, mlda.py:23-33) */
+        double lpt_s = yo_logpost(pb, 2, s, &cs->n_evals[2]);
+        double lpm_s = yo_logpost(pb, 1, s, &cs->n_evals[1]);
+        double delta = lpt_s + cs->lp[1] - lpm_s - cs->lp[2];
+        if (accept_rule(delta, get_uf(ns, n))) {
+            memcpy(cs->theta, s, sizeof(double) * d);
+            cs->lp[0] = lpc_s; cs->lp[1] = lpm_s; cs->lp[2] = lpt_s;
+            cs->n_accept++;
+            return 1;
+        }
+        return 0;
+    }
     double lpf_s = yo_logpost(pb, 1, s, &cs->n_evals[1]);
     double delta = lpf_s + cs->lp[0] - lpc_s - cs->lp[1]; /* mlda.py:148-152, this order */
     if (accept_rule(delta, get_uf(ns, n))) {
@@ -614,17 +640,18 @@ static int chain_step(const yo_problem *pb, chain_state *cs, const noise_src *ns
  *   traj[nc,ns+1,d]  accepted[nc,ns]  lp0/lp1[nc,ns+1]  w_mean/w_var[nc,d] */
 int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
                     const double *theta0, const double *z, const double *u_c, const double *u_f,
-                    double *traj, uint8_t *accepted, double *lp0, double *lp1,
-                    double *w_mean, double *w_var, int64_t *n_evals, int n_threads, double *aem_out)
-{   /* aem_out[nc, 2 + 2 data_dim]: error samples, coarse model evaluations, error mean, error variance */
+                    double *traj, uint8_t *accepted, double *lp0, double *lp1, double *lp2,
+                    double *w_mean, double *w_var, int64_t *n_evals, int n_threads, double *aem_out, double *am_out)
+{   /* aem_out[nc, 2 + 2 data_dim]: error samples, coarse model evaluations, error mean, error variance
+     * am_out[nc, d + 2 d d]: adaptive Metropolis mean, M2, proposal factor L after the last transition */
     const int d = pb->dim, J = pb->J;
-    if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 2) return -1;
+    if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 3) return -1;
     for (int l = 0; l < pb->n_levels; l++) if (pb->model != YO_GAUSS && pb->level[l].data_dim > YO_MAX_DATA) return -1;
-    int64_t ev0 = 0, ev1 = 0;
+    int64_t ev0 = 0, ev1 = 0, ev2 = 0;
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
-    #pragma omp parallel for schedule(dynamic, 1) reduction(+:ev0, ev1)
+    #pragma omp parallel for schedule(dynamic, 1) reduction(+:ev0, ev1, ev2)
     for (int64_t c = 0; c < nc; c++) {
         chain_state cs;
         noise_src nsrc = { z + (size_t)c * ns * J * d, u_c + (size_t)c * ns * J, u_f + (size_t)c * ns, 0, 0, 0 };
@@ -632,7 +659,8 @@ int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
         for (int64_t n = 0; n <= ns; n++) {
             if (traj) memcpy(traj + ((size_t)c * (ns + 1) + n) * d, cs.theta, sizeof(double) * d);
             if (lp0) lp0[(size_t)c * (ns + 1) + n] = cs.lp[0];
-            if (lp1 && pb->n_levels == 2) lp1[(size_t)c * (ns + 1) + n] = cs.lp[1];
+            if (lp1 && pb->n_levels >= 2) lp1[(size_t)c * (ns + 1) + n] = cs.lp[1];
+            if (lp2 && pb->n_levels == 3) lp2[(size_t)c * (ns + 1) + n] = cs.lp[2];
             if (n == ns) break;
             int a = chain_step(pb, &cs, &nsrc, n);
             if (accepted) accepted[(size_t)c * ns + n] = (uint8_t)a;
@@ -641,7 +669,13 @@ int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
             if (w_mean) w_mean[c * d + i] = cs.w_mean[i];
             if (w_var) w_var[c * d + i] = cs.w_n > 1 ? cs.w_m2[i] / (double)(cs.w_n - 1) : NAN;
         }
-        ev0 += cs.n_evals[0]; ev1 += cs.n_evals[1];
+        ev0 += cs.n_evals[0]; ev1 += cs.n_evals[1]; ev2 += cs.n_evals[2];
+        if (am_out && pb->adaptive) {
+            double *o = am_out + (size_t)c * (d + 2 * d * d);
+            memcpy(o, cs.am_mean, sizeof(double) * d);
+            memcpy(o + d, cs.am_m2, sizeof(double) * d * d);
+            memcpy(o + d + d * d, cs.L, sizeof(double) * d * d);
+        }
         if (aem_out && pb->aem) {
             const int dd = pb->level[0].data_dim;
             double *o = aem_out + (size_t)c * (2 + 2 * dd);
@@ -653,7 +687,7 @@ int yo_run_injected(const yo_problem *pb, int64_t nc, int64_t ns,
             }
         }
     }
-    if (n_evals) { n_evals[0] = ev0; n_evals[1] = ev1; }
+    if (n_evals) { n_evals[0] = ev0; n_evals[1] = ev1; n_evals[2] = ev2; }
     return 0;
 }
 
@@ -665,7 +699,7 @@ int yo_run_philox(const yo_problem *pb, int64_t nc, int64_t chain_offset, uint64
                   double *theta, double *traj, int64_t *n_accept, int64_t *n_evals, int n_threads)
 {
     const int d = pb->dim;
-    if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 2) return -1;
+    if (d > YO_MAX_DIM || pb->n_levels < 1 || pb->n_levels > 3) return -1;
     for (int l = 0; l < pb->n_levels; l++) if (pb->model != YO_GAUSS && pb->level[l].data_dim > YO_MAX_DATA) return -1;
     if (thin < 1) thin = 1;
     const int64_t n_out = ns / thin;
@@ -685,7 +719,7 @@ int yo_run_philox(const yo_problem *pb, int64_t nc, int64_t chain_offset, uint64
         }
         memcpy(theta + c * d, cs.theta, sizeof(double) * d);
         if (n_accept) n_accept[c] = cs.n_accept;
-        ev0 += cs.n_evals[0]; ev1 += cs.n_evals[1];
+        ev0 += cs.n_evals[0]; ev1 += cs.n_evals[1] + cs.n_evals[2];
     }
     if (n_evals) { n_evals[0] = ev0; n_evals[1] = ev1; }
     return 0;
@@ -806,19 +840,25 @@ void yo_welford(const double *x, int64_t n, int d, double *mean, double *var)
     free(m2);
 }
 
-/* DenseCovarianceMatrix (covariance.py:69-94): lower Cholesky, L x, C^-1 x */
+/* DenseCovarianceMatrix (covariance.py:69-94): lower Cholesky, L x, C^-1 x.
+ * scipy.linalg.cholesky -> LAPACK dpotrf; for these sizes the unblocked column algorithm (dpotf2):
+ * a_jj = sqrt(c_jj - dot(l_j, l_j)); column below = (c_ij - dot(l_i, l_j)) * (1 / a_jj)  -- the
+ * RECIPROCAL is formed once and multiplied (DSCAL), which rounds differently from a division. */
 int yo_cholesky(const double *C, int d, double *L)
 {
     memset(L, 0, sizeof(double) * d * d);
     for (int j = 0; j < d; j++) {
-        double s = C[j * d + j];
-        for (int k = 0; k < j; k++) s -= L[j * d + k] * L[j * d + k];
+        double dot = 0.0;
+        for (int k = 0; k < j; k++) dot += L[j * d + k] * L[j * d + k];
+        double s = C[j * d + j] - dot;
         if (!(s > 0.0)) return -1;
-        L[j * d + j] = sqrt(s);
+        const double ajj = sqrt(s);
+        L[j * d + j] = ajj;
+        const double rcp = 1.0 / ajj;
         for (int i = j + 1; i < d; i++) {
-            double t = C[i * d + j];
-            for (int k = 0; k < j; k++) t -= L[i * d + k] * L[j * d + k];
-            L[i * d + j] = t / L[j * d + j];
+            double dt = 0.0;
+            for (int k = 0; k < j; k++) dt += L[i * d + k] * L[j * d + k];
+            L[i * d + j] = (C[i * d + j] - dt) * rcp;
         }
     }
     return 0;

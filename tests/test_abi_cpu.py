@@ -31,7 +31,8 @@ def test_abi_version_and_struct_sizes():
     assert lib.yg_abi_version() == _lib.YG_ABI_VERSION
     assert lib.yg_pooled_len(2) == 3 + 2 + 4 + 4 + 2
     # POD layouts the binding mirrors (sizes from the C compiler's rules)
-    assert C.sizeof(_lib.YgLevel) == 8 * 2 + 8 + 8 + 8 * 7 + 8 * 3 + 8
+    assert C.sizeof(_lib.YgLevel) == 8 * 2 + 8 + 8 + 8 * 7 + 8 * 3 + 8 + 8          # ABI 4: + tempering
+    assert C.sizeof(_lib.YgProblem) == 8 + _lib.YG_MAX_LEVELS * C.sizeof(_lib.YgLevel) + 8 + 8 + 8
     assert C.sizeof(_lib.YgConfig) % 8 == 0
 
 
@@ -47,8 +48,14 @@ def test_create_rejects_bad_config_without_touching_the_gpu():
     cfg.dim = 0
     assert lib.yg_create(C.byref(cfg), C.byref(h)) == _lib.YG_ERR_INVALID
     assert b"dim" in lib.yg_last_error()
-    cfg.dim, cfg.n_levels = 2, 3            # >2 levels: reference quirk, out of scope
+    cfg.dim, cfg.n_levels = 2, 4            # three surrogates crash in the reference itself (mlda.py:23-33)
     with pytest.raises(NotImplementedError):
+        _lib.check(lib.yg_create(C.byref(cfg), C.byref(h)))
+    cfg.n_levels, cfg.model, cfg.sub_chain_length = 3, _lib.MODEL_LV, 2      # two surrogates: not on the LV kernel
+    with pytest.raises(NotImplementedError):
+        _lib.check(lib.yg_create(C.byref(cfg), C.byref(h)))
+    cfg.n_levels, cfg.model, cfg.dim, cfg.adaptive = 1, _lib.MODEL_GAUSS, 1, 1
+    with pytest.raises(NotImplementedError, match="scalar chains"):        # chain/adaptive.py:41-43
         _lib.check(lib.yg_create(C.byref(cfg), C.byref(h)))
 
 

@@ -157,7 +157,10 @@ def test_unrecognised_plugins_are_refused_without_fallback():
         lower_problem([MyDensity()], IIDCovarianceMatrix(2, 1.))
     with pytest.raises(NotImplementedError, match="levels"):
         g = GaussianTargetDensity2d(ParameterVector(np.zeros(2)), np.eye(2))
-        lower_problem([g, g, g], IIDCovarianceMatrix(2, 1.))
+        lower_problem([g, g, g, g], IIDCovarianceMatrix(2, 1.))          # three surrogates crash in the reference too
+    g = GaussianTargetDensity2d(ParameterVector(np.zeros(2)), np.eye(2))
+    low = lower_problem([g, g, g], IIDCovarianceMatrix(2, 1.), subChainLength=4)      # two surrogates: mlda.py:112-117
+    assert low.levels == 3 and low.J == 4 and "L2_g_mean" in low.arrays
     with pytest.raises(ValueError, match="centred Gaussian noise"):
         AdditiveGaussianNoiseLikelihood(Data(np.zeros((2, 2))), None, object())
 

@@ -15,6 +15,7 @@ from yagre_mcmc_b200.statistics import (IIDCovarianceMatrix, DiagonalCovarianceM
 from yagre_mcmc_b200.utility import Hierarchy, SharedComponent
 from yagre_mcmc_b200.chain.method import MRWBuilder, MLDABuilder, AMBuilder, PCNBuilder, AEMBuilder
 from yagre_mcmc_b200.statistics import AEMLikelihood
+from yagre_mcmc_b200.chain.target import UnnormalisedPosterior
 from yagre_mcmc_b200.chain.diagnostics import DummyDiagnostics, AcceptanceRateDiagnostics, FullDiagnostics
 from yagre_mcmc_b200.postprocessing.autocorrelation import integrated_autocorrelation, effective_sample_size
 
@@ -97,6 +98,7 @@ def test_pooled_proposal_covariance_through_the_builder():
     L = pooled["prop_L"]
     assert L.shape == (2, 2) and L[0, 1] == 0.0
     last = np.asarray(mc.chain.trajectory)[-1]                                      # [nChains, d]
+    mc.clear()              # diagnostics accumulate across run() until clear(), as in the reference (:122-125)
     mc.run(3000, ParameterVector(last), verbose=False)
     rate1 = mc.diagnostics.global_acceptance_rate()
     assert rate0 > 0.7 and 0.25 < rate1 < 0.45                                      # tiny steps -> tuned steps
@@ -146,15 +148,105 @@ def test_mlda_perfect_surrogate_always_accepts():
     assert abs(mc.diagnostics.global_acceptance_rate() - 1.0) < 1e-3                # test_mlda.py:128-130
 
 
-def test_deeper_hierarchies_are_refused():
-    tgtMean, tgtCov, tgt, sur = _mlda_targets(np.zeros(2), np.eye(2))
+def test_mlda_two_surrogates_through_the_builder():
+    """reference test/test_mlda.py:14-91 (two surrogates, subChainLengths [6, 6]; passes at HEAD): chain length,
+    acceptance in (0.1, 0.9), mean within 0.1 -- here over an ensemble.  Three surrogates crash in the reference
+    (AttributeError in SurrogateTransition) and are refused."""
+    tgtMean = np.array([1.0, 1.5])
+    tgtCov = np.array([[2.4, -0.5], [-0.5, 0.7]])
+    tgt = GaussianTargetDensity2d(ParameterVector(tgtMean), tgtCov)
+    base = GaussianTargetDensity2d(ParameterVector(tgtMean + [-0.05, 0.01]), 3.0 * np.array([[2.8, -0.1], [-0.1, 1.7]]))
+    fine = GaussianTargetDensity2d(ParameterVector(tgtMean + [0.0, -0.01]), 1.5 * np.array([[2.4, -0.3], [-0.3, 1.1]]))
     b = MLDABuilder()
     b.explicitTarget = tgt
-    b.surrogateTargets = [sur, sur]
+    b.surrogateTargets = [base, fine]
     b.baseProposalCovariance = IIDCovarianceMatrix(2, 1.0)
-    b.subChainLengths = [3, 3]
+    b.subChainLengths = [6, 6]
+    b.nChains, b.seed = 512, 42
+    mc = b.build_method()
+    assert mc.nSurrogates == 2
+    mc.run(2000, ParameterVector(np.array([-8.0, -7.0])), verbose=False)
+    states = np.asarray(mc.chain.trajectory)
+    assert states.shape == (2000, 512, 2)
+    assert 0.1 < mc.diagnostics.global_acceptance_rate() < 0.9
+    np.testing.assert_allclose(states[500::5].reshape(-1, 2).mean(0), tgtMean, atol=0.1)
+    np.testing.assert_allclose(np.cov(states[500::5].reshape(-1, 2).T), tgtCov, atol=0.1)
+    coarse, fine_ev = mc.evaluation_counts()
+    assert coarse > 5.9 * 512 * 1999 and fine_ev <= 512 * 1999
+    b.surrogateTargets = [base, fine, fine]
+    b.subChainLengths = [3, 3, 3]
     with pytest.raises(NotImplementedError):
         b.build_method()
+
+
+def test_consecutive_runs_use_fresh_noise_and_diagnostics_accumulate():
+    """the reference's generator keeps advancing across run() calls and its diagnostics accumulate
+    until clear() (chain/metropolisHastings.py:103-125)."""
+    b = MRWBuilder()
+    b.explicitTarget = GaussianTargetDensity2d(ParameterVector(np.array([1.0, 1.5])), np.array([[2.4, -0.5], [-0.5, 0.7]]))
+    b.proposalCovariance = IIDCovarianceMatrix(2, 1.0)
+    b.nChains, b.seed = 64, 3
+    b.diagnostics = FullDiagnostics()
+    mc = b.build_method()
+    start = ParameterVector(np.array([1.0, 1.5]))
+    mc.run(200, start, verbose=False)
+    t1 = np.asarray(mc.chain.trajectory).copy()
+    n1 = mc.ensemble.counters()
+    mc.run(200, start, verbose=False)
+    t2 = np.asarray(mc.chain.trajectory)
+    n2 = mc.ensemble.counters()
+    assert np.array_equal(t1[0], t2[0]) and not np.array_equal(t1[1:], t2[1:])
+    assert n1["step_index"] == 199 and n2["step_index"] == 398
+    assert n2["transitions"] == 2 * n1["transitions"] and n2["welford_n"] == 398          # accumulated
+    mc.clear()
+    mc.run(100, start, verbose=False)
+    n3 = mc.ensemble.counters()
+    assert n3["welford_n"] == 99 and n3["transitions"] == 64 * 99 and n3["step_index"] == 497
+
+
+def test_adaptive_coarse_proposal_through_the_mlda_builder():
+    """Extension: an AdaptiveCovarianceMatrix descriptor as baseProposalCovariance makes the
+    coarse MRW of delayed acceptance adaptive per chain (the reference's AdaptiveMRWProposal as the surrogate's
+    proposal method, pinned by tests/golden/am_mlda_*.npz).  C5 problem through the builders."""
+    from yagre_mcmc_b200.chain.adaptive import AdaptiveCovarianceMatrix
+    meta, arr, hierarchy, lik, prior = _lv_hierarchy()
+    b = MLDABuilder()
+    b.bayesModel = hierarchy
+    b.baseProposalCovariance = AdaptiveCovarianceMatrix(IIDCovarianceMatrix(2, 0.1), idleSteps=30, collectionSteps=150,
+                                                       eps=1e-8, refresh=5)
+    b.subChainLengths = [3]
+    b.nChains, b.seed, b.storeTrajectory = 2048, 11, False
+    mc = b.build_method()
+    th0 = bp.lv_initial_states(2048)
+    mc.run(400, LotkaVolterraParameter(th0), verbose=False)
+    L = mc.proposal_factors()
+    assert L.shape == (2048, 2, 2) and np.all(L[:, 0, 1] == 0.0) and np.all(L[:, 0, 0] < np.sqrt(0.1))
+    assert mc.ensemble.counters()["am_steps"] == 399
+    assert 0.1 <= mc.diagnostics.global_acceptance_rate() <= 0.8
+
+
+def test_tempered_surrogate_through_the_builder():
+    """TemperedUnnormalisedPosterior (reference chain/target.py:25-43) as the explicit surrogate of MLDABuilder."""
+    from yagre_mcmc_b200.chain.target import TemperedUnnormalisedPosterior
+    meta, a = bp.linear_problem(True)
+    noise = CentredGaussianNoise(IIDCovarianceMatrix(2, 0.3))
+    prior = Gaussian(ParameterVector(a["L0_prior_mean"]), IIDCovarianceMatrix(2, 5.0))
+    likC, likF = [AdditiveGaussianNoiseLikelihood(Data(a["L0_data"]), ForwardModel(LinearModelSolver(a[f"L{l}_G"], a[f"L{l}_b"])), noise)
+                  for l in range(2)]
+    b = MLDABuilder()
+    b.explicitTarget = UnnormalisedPosterior(likF, prior)
+    b.surrogateTargets = [TemperedUnnormalisedPosterior(likC, prior, 0.35)]
+    b.baseProposalCovariance = IIDCovarianceMatrix(2, 0.5)
+    b.subChainLengths = [5]
+    b.nChains, b.seed = 4096, 5
+    mc = b.build_method()
+    mc.run(3000, ParameterVector(np.zeros(2)), verbose=False)
+    x = np.asarray(mc.chain.trajectory)[1000::20].reshape(-1, 2)
+    mean, cov = bp.linear_posterior('f')
+    np.testing.assert_allclose(x.mean(0), mean, atol=0.02)           # the fine screen keeps the target exact
+    np.testing.assert_allclose(np.cov(x.T), cov, rtol=0.1, atol=5e-3)
+    with pytest.raises(ValueError):
+        TemperedUnnormalisedPosterior(likC, prior, 1.5)
 
 
 def _lv_hierarchy():

@@ -4,12 +4,12 @@ import numpy as np
 import pytest
 
 from oracle import cport
-from golden_io import load, rel_err, CHAIN_CASES
+from golden_io import load, rel_err, CHAIN_CASES, MLDA3_CASES, AM_CASES, TEMPERED_CASES
 
 LOGPOST_RTOL = 1e-10     # north_star: 1e-10 relative on log-posterior
 
 
-@pytest.mark.parametrize("name", CHAIN_CASES)
+@pytest.mark.parametrize("name", CHAIN_CASES + MLDA3_CASES + TEMPERED_CASES)
 def test_chain_trajectory_matches_reference(name):
     meta, a = load(name)
     pb = cport.Problem(meta, a)
@@ -19,11 +19,43 @@ def test_chain_trajectory_matches_reference(name):
     # trajectories: proposals are s + L z in both, so states agree to rounding
     assert rel_err(out["traj"], a["traj"]).max() <= 1e-13, name
     assert rel_err(out["logpost_L0"], a["logpost_L0"]).max() <= LOGPOST_RTOL, name
-    if meta["levels"] == 2:
+    if meta["levels"] >= 2:
         assert rel_err(out["logpost_L1"], a["logpost_L1"]).max() <= LOGPOST_RTOL, name
+    if meta["levels"] == 3:
+        assert rel_err(out["logpost_L2"], a["logpost_L2"]).max() <= LOGPOST_RTOL, name
     if "welford_mean" in a:     # FullDiagnostics: Welford of the pre-transition state
         np.testing.assert_allclose(out["welford_mean"], a["welford_mean"], rtol=1e-12)
         np.testing.assert_allclose(out["welford_var"], a["welford_var"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", AM_CASES)
+def test_adaptive_metropolis_matches_reference_interface(name):
+    """a14: the unmodified AdaptiveMRWProposal + MetropolisHastings.run (chain/adaptive.py:37-64,
+    chain/metropolisHastings.py:103-120) drove our concrete AdaptiveCovarianceMatrix
+    (oracle/ref_harness.py HaarioAdaptiveCovariance) under injected noise; update() call order, the
+    covariance swap and the Cholesky (scipy / LAPACK dpotf2 order) are therefore the reference's.  Single level
+    (Gaussian target of test/test_adaptive.py, LV) and as the coarse proposal of two-level delayed acceptance.
+    Proposals through a dense factor differ from numpy's `L @ z` by at most an ulp (BLAS fuses the dot product),
+    hence 1e-12 instead of bitwise."""
+    meta, a = load(name)
+    out = cport.run_injected(cport.Problem(meta, a), a["theta0"], a["z"], a["u_c"], a["u_f"])
+    assert np.array_equal(out["accepted"], a["accepted"]), name
+    assert rel_err(out["traj"], a["traj"]).max() <= 1e-12, name
+    assert rel_err(out["logpost_L0"], a["logpost_L0"]).max() <= LOGPOST_RTOL, name
+    if meta["levels"] == 2:
+        assert rel_err(out["logpost_L1"], a["logpost_L1"]).max() <= LOGPOST_RTOL, name
+    np.testing.assert_allclose(out["am_mean"], a["am_mean"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(out["am_m2"], a["am_m2"], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(out["am_L"], a["am_L"], rtol=1e-11, atol=1e-14)
+    assert np.all(a["am_refreshes"] > 0) and np.all(a["am_L"][:, 1, 0] != 0.0)      # the factor did switch
+
+
+def test_three_level_fixture_ignores_the_first_sub_chain_length():
+    """mlda.py:112-117: with two surrogates the MRW sub-chain has subChainLengths[1] steps; [0] is ignored."""
+    meta, a = load("mlda3_gauss2d_hier")
+    assert meta["subChainLengths"] == [9, 4] and meta["J"] == 4 and a["z"].shape[2] == 4
+    for order in meta["rng_order"]:
+        assert order.count('N') == 4 * a["u_f"].shape[1]
 
 
 @pytest.mark.parametrize("name", ["aem_linear", "aem_linear_noheuristic"])

@@ -1,0 +1,336 @@
+"""GPU: stream position across runs, adaptive Metropolis on the Lotka-Volterra kernels, MLDA with two
+surrogates, tempered surrogates, the headline launch geometry replayed directly, degenerate IAT series."""
+import numpy as np
+import pytest
+import torch
+
+import bench_problems as bp
+from golden_io import load, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOGPOST_RTOL = 1e-10      # north_star: 1e-10 relative on log-posterior
+
+
+def _ens(meta, arrays, nc, **kw):
+    from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem
+    return ChainEnsemble(LoweredProblem(meta, arrays), nc, **kw)
+
+
+def _replay(meta, arrays, th0, out, rows=None, adaptive=None):
+    from oracle import cport
+    z = out["z"].cpu().numpy().transpose(3, 0, 1, 2)
+    u_c = np.nan_to_num(out["u_c"].cpu().numpy().transpose(2, 0, 1), nan=0.5)
+    u_f = np.nan_to_num(out["u_f"].cpu().numpy().transpose(1, 0), nan=0.5)
+    if rows is not None:
+        z, u_c, u_f, th0 = z[rows], u_c[rows], u_f[rows], th0[rows]
+    return cport.run_injected(cport.Problem(meta, arrays, adaptive=adaptive), th0, z, u_c, u_f)
+
+
+# ------------------------------------------------------------------------------------------
+# the noise stream keeps advancing across set_state
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["linear_two_level", "gauss2d", "lv_two_level"])
+def test_stream_position_survives_set_state(case):
+    """yg_set_state does not rewind the Philox stream (the reference's numpy generator keeps advancing across
+    run() calls): two runs from the same state differ, restart + run(N) equals a single run(2N), and yg_seek
+    rewinds explicitly."""
+    if case == "linear_two_level":
+        (meta, arrays), th0, n = bp.linear_problem(True), np.zeros((300, 2)), 40
+    elif case == "gauss2d":
+        (meta, arrays), th0, n = bp.gauss2d_problem(), np.tile([-8.0, -7.0], (300, 1)), 40
+    else:
+        (meta, arrays), th0, n = bp.lv_problem(True), bp.lv_initial_states(300), 12
+    nc = th0.shape[0]
+    a = _ens(meta, arrays, nc, seed=5)
+    a.set_state(th0)
+    r1 = a.run(n, samples=True)["samples"].clone()
+    assert a.counters()["step_index"] == n
+    a.set_state(th0)                                           # same start, stream NOT rewound
+    r2 = a.run(n, samples=True)["samples"].clone()
+    assert a.counters()["step_index"] == 2 * n and a.counters()["welford_n"] == n
+    assert not torch.equal(r1, r2)
+    a.set_state(th0, step_index=0)                             # explicit rewind: the first realisation again
+    r3 = a.run(n, samples=True)["samples"]
+    assert torch.equal(r1, r3)
+    # restart from the end of r1 + run(n)  ==  run(2n) in one go
+    b = _ens(meta, arrays, nc, seed=5)
+    b.set_state(th0)
+    full = b.run(2 * n, samples=True)["samples"]
+    assert torch.equal(full[:n], r1)
+    c = _ens(meta, arrays, nc, seed=5)
+    c.set_state(th0)
+    c.run(n, samples=False)
+    end = c.state()["theta"].t().contiguous()
+    c.set_state(end, keep_diagnostics=True)
+    assert c.counters()["welford_n"] == n
+    second = c.run(n, samples=True)["samples"]
+    if case == "lv_two_level":
+        # the restart re-evaluates log pi(state) with the one-thread-per-parameter evaluator; the LV step kernel
+        # carries the value its own (differently ordered, few-ulp) evaluation produced: equal to rounding
+        assert rel_err(second.cpu().numpy(), full[n:].cpu().numpy()).max() <= 1e-12
+    else:
+        assert torch.equal(second, full[n:])
+    st_c, st_b = c.state(), b.state()
+    assert st_c["welford_n"] == st_b["welford_n"] == 2 * n
+    np.testing.assert_allclose(st_c["w_mean"].cpu().numpy(), st_b["w_mean"].cpu().numpy(), rtol=1e-12)
+    assert torch.equal(st_c["n_accept"], st_b["n_accept"]) or case == "lv_two_level"
+
+
+def test_keep_flags_control_what_a_restart_resets():
+    meta, arrays = bp.gauss2d_problem()
+    nc = 128
+    ad = dict(idle=5, collection=20, eps=1e-4)
+    e = _ens(meta, arrays, nc, seed=3, adaptive=ad)
+    th0 = np.tile([-8.0, -7.0], (nc, 1))
+    e.set_state(th0)
+    e.run(60, samples=False)
+    s0 = e.state()
+    assert s0["am_steps"] == 60 and not torch.allclose(s0["prop_L"][0, 0], torch.ones(nc, dtype=torch.float64, device="cuda"))
+    e.set_state(th0, keep_adaptation=True)                     # diagnostics restart, adaptation continues
+    s1 = e.state()
+    assert s1["welford_n"] == 0 and int(s1["n_accept"].sum()) == 0 and s1["am_steps"] == 60
+    assert torch.equal(s1["prop_L"], s0["prop_L"]) and torch.equal(s1["am_m2"], s0["am_m2"])
+    e.run(10, samples=False)
+    e.set_state(th0, keep_diagnostics=True)                    # adaptation restarts, diagnostics continue
+    s2 = e.state()
+    assert s2["welford_n"] == 10 and s2["am_steps"] == 0
+    assert torch.equal(s2["prop_L"][0, 0], torch.ones(nc, dtype=torch.float64, device="cuda"))
+    assert float(s2["am_m2"].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# adaptive Metropolis on the LV kernels
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("two_level", [True, False])
+def test_lv_adaptive_philox_run_replayed_through_oracle(two_level):
+    """Multi-CTA, multi-segment launch (Nf = 512 > 128-step segments) with per-chain adaptation: recorded noise
+    replayed through the oracle, whose recurrence is pinned to the reference interface (am_*.npz)."""
+    meta, arrays = bp.lv_problem(two_level)
+    ad = dict(idle=6, collection=15, eps=1e-6, refresh=2)
+    nc, ns = 700, 30
+    th0 = bp.lv_initial_states(nc)
+    ens = _ens(meta, arrays, nc, seed=31, adaptive=ad)
+    ens.set_state(th0)
+    out = ens.run(ns, samples=True, accepted=True, logpost=True, record=True)
+    torch.cuda.synchronize()
+    ref = _replay(meta, arrays, th0, out, adaptive=ad)
+    acc = out["accepted"].cpu().numpy().T
+    assert int((acc != ref["accepted"]).sum()) == 0
+    traj = out["samples"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(traj, ref["traj"][:, 1:]).max() <= 1e-12
+    lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, -1], ref["logpost_L1" if two_level else "logpost_L0"][:, 1:]).max() <= LOGPOST_RTOL
+    st = ens.state()
+    np.testing.assert_allclose(st["am_mean"].cpu().numpy().T, ref["am_mean"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(st["am_m2"].permute(2, 0, 1).cpu().numpy(), ref["am_m2"], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(st["prop_L"].permute(2, 0, 1).cpu().numpy(), ref["am_L"], rtol=1e-11, atol=1e-15)
+    assert np.all(ref["am_L"][:, 1, 0] != 0.0)
+
+
+def test_lv_adaptive_resume_is_bit_exact():
+    meta, arrays = bp.lv_problem(True)
+    ad = dict(idle=4, collection=10, eps=1e-6)
+    nc = 200
+    th0 = bp.lv_initial_states(nc)
+    a = _ens(meta, arrays, nc, seed=8, adaptive=ad)
+    a.set_state(th0)
+    ra = a.run(24, samples=True)["samples"]
+    b = _ens(meta, arrays, nc, seed=8, adaptive=ad)
+    b.set_state(th0)
+    b.run(12, samples=False)
+    c = _ens(meta, arrays, nc, seed=8, adaptive=ad)
+    c.load_state(b.state())
+    rc = c.run(12, samples=True)["samples"]
+    assert torch.equal(ra[12:], rc)
+    sa, sc = a.state(), c.state()
+    for k in ("am_mean", "am_m2", "prop_L", "w_mean", "w_m2", "n_accept", "logpost"):
+        assert torch.equal(sa[k], sc[k]), k
+    assert sa["am_steps"] == sc["am_steps"] == 24
+
+
+@pytest.mark.parametrize("two_level", [True, False])
+def test_lv_adaptive_posterior_moments_and_acceptance(two_level):
+    """C5 / C4 with a per-chain adaptive (coarse) proposal against the long runs of the unmodified reference
+    (lv_long_*.npz), with the thresholds of the reference's skipped test/test_adaptive.py:24-27,51,72,90:
+    mean atol 0.03, covariance atol 0.05, acceptance in [0.1, 0.8]."""
+    _, g = load("lv_long_twoLevel" if two_level else "lv_long_singleLevel")
+    meta, arrays = bp.lv_problem(two_level)
+    nc = 8192
+    ens = _ens(meta, arrays, nc, seed=77, adaptive=dict(idle=50, collection=200, eps=1e-8, refresh=5))
+    ens.set_state(bp.lv_initial_states(nc))
+    ens.run(600, samples=False)
+    c0 = ens.counters()
+    s = ens.run(300, thin=10, samples=True)["samples"].cpu().numpy()      # [30, d, nc]
+    c1 = ens.counters()
+    flat = s.transpose(0, 2, 1).reshape(-1, 2)
+    np.testing.assert_allclose(flat.mean(0), g["mean"], atol=0.03)
+    np.testing.assert_allclose(np.cov(flat.T), g["cov"], atol=0.05)
+    rate = (c1["accepted"] - c0["accepted"]) / (c1["transitions"] - c0["transitions"])
+    assert 0.1 <= rate <= 0.8
+    # adapted proposal ~ 2.4^2/d x the covariance the coarse MRW explores (posterior-sized, not the initial 0.1 I)
+    L = ens.state()["prop_L"].cpu().numpy()
+    C = np.einsum('ikc,jkc->ijc', L, L).mean(axis=2)
+    assert np.all(np.diag(C) < 0.1) and np.all(np.diag(C) > 0.2 * 2.88 * np.diag(g["cov"]))
+
+
+# ------------------------------------------------------------------------------------------
+# the headline launch geometry, replayed directly
+# ------------------------------------------------------------------------------------------
+def test_headline_geometry_direct_replay():
+    """65,536 chains x 50 transitions in ONE launch of the bench geometry (148 CTAs x 768 threads, ~443 chains per
+    CTA, four 128-step segments per fine integration): noise recorded on the device, 256 randomly chosen chains
+    replayed through the oracle -- identical decisions, log-posterior within 1e-10."""
+    meta, arrays = bp.lv_problem(True)
+    nc, ns = 65536, 50
+    th0 = bp.lv_initial_states(nc)
+    ens = _ens(meta, arrays, nc, seed=20261018)
+    ens.set_state(th0)
+    out = ens.run(ns, samples=True, accepted=True, logpost=True, record=True)
+    torch.cuda.synchronize()
+    launch = ens.last_launch()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert launch["grid"] == sms and launch["block"] == 768
+    rows = np.sort(np.random.default_rng(5).choice(nc, 256, replace=False))
+    idx = torch.from_numpy(rows).to("cuda")
+    sub = {k: out[k].index_select(out[k].dim() - 1, idx) for k in ("z", "u_c", "u_f", "samples", "accepted", "logpost")}
+    ref = _replay(meta, arrays, th0[rows], sub)
+    acc = sub["accepted"].cpu().numpy().T
+    assert int((acc != ref["accepted"]).sum()) == 0
+    traj = sub["samples"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(traj, ref["traj"][:, 1:]).max() <= 1e-12
+    lp = sub["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, 0], ref["logpost_L0"][:, 1:]).max() <= LOGPOST_RTOL
+    assert rel_err(lp[:, :, 1], ref["logpost_L1"][:, 1:]).max() <= LOGPOST_RTOL
+    assert 0.2 < acc.mean() < 0.6
+
+
+# ------------------------------------------------------------------------------------------
+# MLDA with two surrogates / tempered surrogate: Philox runs replayed, statistics
+# ------------------------------------------------------------------------------------------
+def _three_level_gauss():
+    _, a = load("mlda3_gauss2d")
+    arrays = {k: a[k] for k in a if k.startswith(("L0_", "L1_", "L2_")) or k == "prop_L"}
+    return dict(model="gauss", dim=2, levels=3, J=6, eq="exact"), arrays
+
+
+def test_three_level_philox_run_replayed_through_oracle():
+    meta, arrays = _three_level_gauss()
+    nc, ns = 1000, 200
+    th0 = np.tile([-8.0, -7.0], (nc, 1))
+    for seed, record in ((4, True), (4, False)):
+        ens = _ens(meta, arrays, nc, seed=seed)
+        ens.set_state(th0)
+        out = ens.run(ns, samples=True, accepted=True, logpost=True, record=record)
+        if record:
+            ref = _replay(meta, arrays, th0, out)
+            acc = out["accepted"].cpu().numpy().T
+            assert int((acc != ref["accepted"]).sum()) == 0
+            traj = out["samples"].cpu().numpy().transpose(2, 0, 1)
+            assert rel_err(traj, ref["traj"][:, 1:]).max() <= 1e-12
+            lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+            for l in range(3):
+                assert rel_err(lp[:, :, l], ref[f"logpost_L{l}"][:, 1:]).max() <= LOGPOST_RTOL
+            c = ens.counters()
+            ev = ref["n_evals"]
+            assert (c["coarse_evals"], c["mid_evals"], c["fine_evals"]) == (int(ev[0]) - nc, int(ev[1]) - nc, int(ev[2]) - nc)
+            keep = out
+        else:       # the warp-specialised small-ensemble kernel (Philox, <= 32,768 chains) is bit-identical
+            assert ens.last_launch()["block"] == 64
+            for k in ("samples", "accepted", "logpost"):
+                assert torch.equal(out[k], keep[k]), k
+
+
+def test_three_level_posterior_moments():
+    """reference test/test_mlda.py:62-91 (two surrogates, [6, 6]): acceptance in (0.1, 0.9), mean within 0.1."""
+    meta, arrays = _three_level_gauss()
+    nc = 4096
+    ens = _ens(meta, arrays, nc, seed=42)
+    ens.set_state(np.tile([-8.0, -7.0], (nc, 1)))
+    ens.run(500, samples=False)
+    c0 = ens.counters()
+    s = ens.run(400, thin=5, samples=True)["samples"].cpu().numpy()
+    c1 = ens.counters()
+    flat = s.transpose(0, 2, 1).reshape(-1, 2)
+    np.testing.assert_allclose(flat.mean(0), [1.0, 1.5], atol=0.02)
+    np.testing.assert_allclose(np.cov(flat.T), [[2.4, -0.5], [-0.5, 0.7]], atol=0.05)
+    assert 0.1 < (c1["accepted"] - c0["accepted"]) / (c1["transitions"] - c0["transitions"]) < 0.9
+
+
+def test_tempered_surrogate_philox_replay():
+    meta, a = load("mlda_linear_tempered")
+    arrays = {k: a[k] for k in a if k.startswith(("L0_", "L1_")) or k == "prop_L"}
+    nc, ns = 500, 150
+    th0 = np.zeros((nc, 2))
+    ens = _ens(meta, arrays, nc, seed=6)
+    ens.set_state(th0)
+    out = ens.run(ns, samples=True, accepted=True, logpost=True, record=True)
+    ref = _replay(meta, arrays, th0, out)
+    assert int((out["accepted"].cpu().numpy().T != ref["accepted"]).sum()) == 0
+    lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, 0], ref["logpost_L0"][:, 1:]).max() <= LOGPOST_RTOL
+    # the tempered surrogate is flatter than the untempered one: a different coarse log-posterior
+    plain = dict(arrays); plain.pop("L0_tempering")
+    e2 = _ens(meta, plain, 4, seed=6)
+    e2.set_state(np.full((4, 2), 0.3))
+    e3 = _ens(meta, arrays, 4, seed=6)
+    e3.set_state(np.full((4, 2), 0.3))
+    assert not torch.allclose(e2.state()["logpost"][0], e3.state()["logpost"][0])
+    assert torch.equal(e2.state()["logpost"][1], e3.state()["logpost"][1])
+
+
+def test_lv_tempered_level_through_logpost():
+    """The LV kernels apply the tempering factor too: tempering * logL + logprior against the oracle."""
+    from oracle import cport
+    meta, arrays = bp.lv_problem(True)
+    arrays = dict(arrays); arrays["L0_tempering"] = np.array(0.4)
+    nc, ns = 64, 20
+    th0 = bp.lv_initial_states(nc)
+    ens = _ens(meta, arrays, nc, seed=2)
+    ens.set_state(th0)
+    pb = cport.Problem(meta, arrays)
+    want = np.array([cport.logpost(pb, 0, t) for t in th0])
+    np.testing.assert_allclose(ens.state()["logpost"][0].cpu().numpy(), want, rtol=LOGPOST_RTOL)
+    out = ens.run(ns, samples=True, accepted=True, logpost=True, record=True)
+    ref = _replay(meta, arrays, th0, out)
+    assert int((out["accepted"].cpu().numpy().T != ref["accepted"]).sum()) == 0
+    lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, 0], ref["logpost_L0"][:, 1:]).max() <= LOGPOST_RTOL
+
+
+def test_unsupported_combinations_are_refused():
+    meta, arrays = bp.lv_problem(True)
+    m3 = dict(meta, levels=3)
+    a3 = dict(arrays)
+    a3.update({k.replace("L1_", "L2_"): v for k, v in arrays.items() if k.startswith("L1_")})
+    with pytest.raises(NotImplementedError):                   # three levels: one-chain-per-thread kernels only
+        _ens(m3, a3, 8)
+    bm, ba = bp.big_linear_problem(16, 24, 2)
+    with pytest.raises(NotImplementedError):                   # no adaptive proposal on the tensor path
+        _ens(bm, ba, 8, adaptive=dict(idle=1, collection=2))
+    with pytest.raises(NotImplementedError):                   # no adaptive error model on the tensor path
+        bm2, ba2 = bp.big_linear_problem(16, 24, 2, two_level=True, J=2)
+        _ens(bm2, ba2, 8, aem=dict(min_data=3, heuristic=False))
+
+
+# ------------------------------------------------------------------------------------------
+# IAT of degenerate series
+# ------------------------------------------------------------------------------------------
+def test_iat_constant_series_reports_zero_ess():
+    from yagre_mcmc_b200.ensemble import iat_ess
+    rng = np.random.default_rng(0)
+    ns, nc = 400, 6
+    x = rng.standard_normal((ns, 2, nc))
+    x[:, :, 1] = 3.25                      # a stuck chain: constant in every coordinate
+    x[:, 0, 3] = -1.0                      # constant in one coordinate only
+    x[5, 1, 4] = np.inf                    # non-finite sample
+    s = torch.from_numpy(x).cuda()
+    for method in ("max", "mean"):
+        iat, ess = iat_ess(s, method)
+        iat, ess = iat.cpu().numpy(), ess.cpu().numpy()
+        assert iat[1] == ns and ess[1] == 0
+        assert iat[4] == ns and ess[4] == 0
+        if method == "max":
+            assert iat[3] == ns and ess[3] == 0
+        for c in (0, 2, 5):
+            assert 1 <= iat[c] < 10 and ess[c] == ns // iat[c]

@@ -9,7 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyagre_b200.so")
 
-YG_ABI_VERSION = 3
+YG_ABI_VERSION = 4
+YG_MAX_LEVELS = 3
+KEEP_DIAGNOSTICS, KEEP_ADAPTATION = 1, 2
 YG_MAX_DIM = 8
 YG_MAX_DATA_DIM = 8
 YG_BIG_MAX_DIM = 64
@@ -34,11 +36,11 @@ class YgLevel(C.Structure):
                 ("data", _dp), ("noise_prec", _dp), ("prior_mean", _dp), ("prior_prec", _dp),
                 ("G", _dp), ("b", _dp), ("design", _dp),
                 ("alpha", C.c_double), ("gamma", C.c_double), ("T", C.c_double),
-                ("rk4_steps", C.c_int32), ("_pad", C.c_int32)]
+                ("rk4_steps", C.c_int32), ("tempered", C.c_int32), ("tempering", C.c_double)]
 
 
 class YgProblem(C.Structure):
-    _fields_ = [("prop_L", _dp), ("level", YgLevel * 2),
+    _fields_ = [("prop_L", _dp), ("level", YgLevel * YG_MAX_LEVELS),
                 ("proposal", C.c_int32), ("_pad", C.c_int32), ("pcn_step", C.c_double), ("pcn_mean", _dp)]
 
 
@@ -79,11 +81,12 @@ SYMBOLS = {
     "yg_create": (C.c_int, [C.POINTER(YgConfig), C.POINTER(C.c_void_p)]),
     "yg_destroy": (C.c_int, [C.c_void_p]),
     "yg_set_problem": (C.c_int, [C.c_void_p, C.POINTER(YgProblem)]),
-    "yg_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yg_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "yg_seek": (C.c_int, [C.c_void_p, C.c_int64]),
     "yg_set_proposal_factor": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "yg_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(YgOutputs), C.POINTER(YgNoise), C.c_void_p]),
     "yg_get_state": (C.c_int, [C.c_void_p, C.POINTER(YgState), C.c_void_p]),
-    "yg_load_state": (C.c_int, [C.c_void_p, C.POINTER(YgState), C.c_int64, C.c_int64, C.c_void_p]),
+    "yg_load_state": (C.c_int, [C.c_void_p, C.POINTER(YgState), C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "yg_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "yg_logpost": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "yg_iat_ess": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_double,

@@ -18,12 +18,14 @@ def _lower_density(density):
 
 def lower_problem(targets, proposalCov, subChainLength=None, equality='exact', proposal='mrw', pcnStep=None,
                   pcnMean=None):
-    """targets: [target] (MRW) or [surrogate, target] (two-level delayed acceptance)."""
-    if len(targets) not in (1, 2):
+    """targets: [target] (MRW), [surrogate, target] (two-level delayed acceptance) or
+    [base surrogate, finest surrogate, target] (MLDA with two surrogates as the reference runs it,
+    mlda.py:12-43,60-71,112-117: sub-chain on the base surrogate, screen with the finest one)."""
+    if len(targets) not in (1, 2, 3):
         raise NotImplementedError(
-            f"{len(targets)} levels requested: the device implements single-level MRW and two-level delayed "
-            "acceptance (one surrogate); deeper MLDA hierarchies follow a quirky recursion in the reference "
-            "(mlda.py:23-33,112-117) and are out of scope")
+            f"{len(targets)} levels requested: the device implements MRW, two-level delayed acceptance and MLDA "
+            "with two surrogates; the reference itself crashes for 3 and 5 surrogates "
+            "(AttributeError in SurrogateTransition, mlda.py:23-33)")
     lowered = [_lower_density(t) for t in targets]
     models = {m for m, _ in lowered}
     if len(models) != 1:

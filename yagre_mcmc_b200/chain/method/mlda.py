@@ -1,18 +1,25 @@
-"""Two-level delayed acceptance (reference: yagremcmc/chain/method/mlda.py:76-344, the
-`nSurrogates == 1` branch :102-110 and MLDA._acceptance_probability :146-154).
+"""Multi-level delayed acceptance (reference: yagremcmc/chain/method/mlda.py:12-344).
 
-Per fine step the device runs subChainLengths[0] coarse MRW steps from the current state,
-skips the fine model when the sub-chain did not move (metropolisHastings.py:60-61), and
-otherwise screens the sub-chain's end point with
+One surrogate (`nSurrogates == 1` branch :102-110, MLDA._acceptance_probability :146-154): per fine step
+the device runs subChainLengths[0] coarse MRW steps from the current state, skips the fine model when the
+sub-chain did not move (metropolisHastings.py:60-61), and otherwise screens the sub-chain's end point with
     min(1, exp(pi_f(p) + pi_c(s) - pi_c(p) - pi_f(s))).
-Deeper hierarchies are refused (NotImplementedError): the reference's recursion for >= 2
-surrogates ignores subChainLengths[0] and crashes for 3 and 5 surrogates."""
+Two surrogates, exactly what the reference does (:12-43,60-71,112-117; pinned by tests/golden/mlda3_*.npz):
+MLDAProposal hands the state to the top SurrogateTransition, whose generate_proposal() runs the BASE MRW
+for subChainLengths[1] steps (subChainLengths[0] is never read) and returns its end point; the screen is
+MLDA._acceptance_probability with the FINEST surrogate as pi_c.  Three and five surrogates crash in the
+reference (AttributeError: MetropolisedRandomWalk has no set_state), four are not implemented here.
+
+Extension: `baseProposalCovariance` may be an AdaptiveCovarianceMatrix descriptor (chain/adaptive.py); the
+coarse MRW then adapts per chain on the device -- the reference's AdaptiveMRWProposal as the proposal method
+of the surrogate MRW, update() before every coarse proposal (pinned by tests/golden/am_mlda_*.npz)."""
 from ..metropolisHastings import MetropolisHastings
 from ..proposal import ProposalMethod
 from ..target import UnnormalisedPosterior
 from ..builder import ChainBuilder
 from ..diagnostics import AcceptanceRateDiagnostics, DummyDiagnostics
 from ..lowering import lower_problem
+from ..adaptive import AdaptiveCovarianceMatrix
 from ...utility.hierarchy import Hierarchy
 
 
@@ -48,16 +55,29 @@ class MLDA(MetropolisHastings):
     def __init__(self, targetDensity, surrogateDensities, baseProposalCov, nSteps, targetDiagnostics,
                  surrogateDiagnosticsList, nChains=1, seed=0, device=None, thin=1, storeTrajectory=True,
                  launch=None, equality='exact', aem=None):
-        if len(surrogateDensities) != 1:
+        nSur = len(surrogateDensities)
+        if nSur not in (1, 2):
             raise NotImplementedError(
-                f"{len(surrogateDensities)} surrogates: only two-level delayed acceptance runs on the device")
-        lowered = lower_problem([surrogateDensities[0], targetDensity], baseProposalCov,
-                                subChainLength=nSteps[0], equality=equality)
+                f"{nSur} surrogates: the device runs MLDA with one or two surrogates (the reference crashes for "
+                "three and five, mlda.py:23-33)")
+        # mlda.py:100-117: one surrogate -> subChainLengths[0] MRW steps; two -> the top SurrogateTransition
+        # runs the base MRW for ITS length subChainLengths[1]
+        J = nSteps[0] if nSur == 1 else nSteps[1]
+        adaptive, cov = None, baseProposalCov
+        if isinstance(baseProposalCov, AdaptiveCovarianceMatrix):
+            adaptive, cov = baseProposalCov.device_config(), baseProposalCov.covariance
+        levels = list(surrogateDensities) + [targetDensity]
+        lowered = lower_problem(levels, cov, subChainLength=J, equality=equality)
         proposal = MLDAProposal(surrogateDensities, baseProposalCov, nSteps)
         super().__init__(targetDensity, proposal, targetDiagnostics, lowered, nChains=nChains, seed=seed,
-                         device=device, thin=thin, storeTrajectory=storeTrajectory, launch=launch, aem=aem)
+                         device=device, thin=thin, storeTrajectory=storeTrajectory, launch=launch, aem=aem,
+                         adaptive=adaptive)
         self._surrogateDiagnostics = surrogateDiagnosticsList
-        for lvl, t in enumerate([surrogateDensities[0], targetDensity]):
+        if any(not isinstance(dg, DummyDiagnostics) for dg in (surrogateDiagnosticsList or [])):
+            import warnings
+            warnings.warn("surrogate diagnostics are not fed by the device: coarse sub-chains live inside the "
+                          "step kernels; evaluation_counts() reports the coarse forward evaluations", stacklevel=3)
+        for lvl, t in enumerate(levels):
             if isinstance(t, UnnormalisedPosterior):
                 t.bind(self._ensemble, lvl)
 
@@ -72,6 +92,10 @@ class MLDA(MetropolisHastings):
         """Forward evaluations actually performed (coarse, fine) -- skipped ones do not count."""
         c = self._ensemble.counters()
         return c['coarse_evals'], c['fine_evals']
+
+    def proposal_factors(self):
+        """Current per-chain coarse proposal factors L [nChains_local, d, d] (adaptive base covariance only)."""
+        return self._ensemble.state()['prop_L'].permute(2, 0, 1).cpu().numpy()
 
 
 class MLDABuilder(ChainBuilder):

@@ -51,6 +51,8 @@ class MetropolisHastings:
         self._ensemble = ChainEnsemble(lowered, self._nLocal, device=device, seed=self._seed,
                                        chain_offset=self._offset, adaptive=adaptive, aem=aem, **(launch or {}))
         self._last = None
+        self._ran = False               # a run() has set the device state at least once
+        self._diagnosticsCleared = True  # clear() was called since the last run(): restart the device accumulators
 
     # ---- reference surface ------------------------------------------------------------------
     @property
@@ -78,8 +80,12 @@ class MetropolisHastings:
         return self._offset, self._offset + self._nLocal
 
     def clear(self):
+        """reference chain/metropolisHastings.py:122-125: resets diagnostics and trajectory.  The device
+        accumulators (accept counters, Welford moments) restart with the next run(); the state of an adaptive
+        proposal / adaptive error model lives as long as the object, as in the reference."""
         self._diagnostics.reset()
         self._chain.clear()
+        self._diagnosticsCleared = True
 
     def run(self, chainLength, initialState, verbose=True):
         chainLength = int(chainLength)
@@ -98,7 +104,13 @@ class MetropolisHastings:
         else:
             raise ValueError(f"initial state must be [{d}] or [{self._nGlobal}, {d}], got {coef.shape}")
         ens = self._ensemble
-        ens.set_state(np.ascontiguousarray(theta0))
+        # Like the reference, a further run() restarts only the chain: diagnostics accumulate until clear()
+        # (metropolisHastings.py:107-108,122-125), adaptation state persists, and the noise stream keeps
+        # advancing (numpy's global generator there, the Philox step index here) -- two runs from the same
+        # state are different realisations.
+        ens.set_state(np.ascontiguousarray(theta0), keep_diagnostics=self._ran and not self._diagnosticsCleared,
+                      keep_adaptation=self._ran)
+        self._ran, self._diagnosticsCleared = True, False
         self._verbosityController.on = bool(verbose)
         nTrans = chainLength - 1
         thin = self._thin
@@ -134,7 +146,7 @@ class MetropolisHastings:
         st = ens.state()
         d = self._lowered.dim
         w_m2 = st['w_m2']
-        stats = dict(n_accept=st['n_accept'].cpu().numpy(), transitions=st['step_index'],
+        stats = dict(n_accept=st['n_accept'].cpu().numpy(), transitions=st['welford_n'],
                      welford_n=st['welford_n'], w_mean=st['w_mean'].t().cpu().numpy(),
                      w_m2_diag=(torch.stack([w_m2[i, i] for i in range(d)], dim=1) if w_m2.dim() == 3
                                 else w_m2.t()).cpu().numpy(),
@@ -149,8 +161,8 @@ class MetropolisHastings:
 
     def pool_proposal_covariance(self, scale=None, eps=1e-8):
         """Optional pooled proposal covariance: replaces the proposal covariance of every chain (all ranks) by
-        scale * (covariance pooled over all chains since the last run() started + eps I), scale = 2.4^2 / d by
-        default.  The idiom mirrors the reference's burn-in restart
+        scale * (covariance pooled over all chains since the diagnostics were last cleared + eps I), scale =
+        2.4^2 / d by default.  The idiom mirrors the reference's burn-in restart
         (example_inference_linearModel_twoLevel.py:228,236): run a burn-in, pool, run again from
         chain.trajectory[-1].  Returns the pooled moments with the new factor under 'prop_L'."""
         from ..parallel import pooled_proposal_covariance

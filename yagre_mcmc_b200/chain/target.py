@@ -1,6 +1,7 @@
 """Unnormalised posterior (reference: yagremcmc/chain/target.py:4-22): log-likelihood + log-prior
-density.  Tempered / bias-corrected variants (:25-67) are out of scope (broken in the
-reference).
+density, and its tempered variant (:25-43): tempering * log-likelihood + log-prior.  BiasCorrection
+(:46-67) is not mirrored: it crashes in the reference (it passes a raw array where a parameter object is
+expected).
 
 evaluate_log() is served by the device (yg_logpost) once a sampler has bound the target."""
 import numpy as np
@@ -40,4 +41,28 @@ class UnnormalisedPosterior(DensityInterface):
         model, lvl = self._likelihood.device_level()
         lvl['prior_mean'] = np.asarray(self._prior.mean.coefficient, dtype=np.float64).reshape(-1)
         lvl['prior_prec'] = self._prior.covariance.precision()
+        return model, lvl
+
+
+class TemperedUnnormalisedPosterior(UnnormalisedPosterior):
+    """reference chain/target.py:25-43.  Usable as an explicit (surrogate) target of MLDABuilder; the
+    reference's TemperedMLDA wrapper itself (chain/method/tmlda.py:44-52) cannot be constructed."""
+
+    def __init__(self, likelihood, prior, tempering):
+        super().__init__(likelihood, prior)
+        self.tempering = tempering
+
+    @property
+    def tempering(self):
+        return self._tempering
+
+    @tempering.setter
+    def tempering(self, value):
+        if not 0.0 <= float(value) <= 1.0:          # chain/method/tmlda.py:24-29
+            raise ValueError(f"Invalid tempering parameter: {value} (must be in [0, 1]).")
+        self._tempering = float(value)
+
+    def device_level(self):
+        model, lvl = super().device_level()
+        lvl['tempering'] = np.array(self._tempering)
         return model, lvl

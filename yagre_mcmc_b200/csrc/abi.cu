@@ -66,6 +66,7 @@ RunArgs make_args(yg_ensemble *e)
     a.seed = e->cfg.seed;
     a.step0 = e->step_index;
     a.welford_n0 = e->welford_n;
+    a.am_t0 = e->am_steps;
     a.theta = e->theta;
     a.logpost = e->logpost;
     a.n_accept = e->n_accept;
@@ -110,10 +111,16 @@ bool is_diagonal(const double *M, int n)
 int set_problem_big(yg_ensemble *e, const yg_problem *pb)
 {
     const int d = e->cfg.dim, nl = e->cfg.n_levels;
-    if (pb->proposal != YG_PROPOSAL_MRW || e->cfg.adaptive || e->cfg.eq_mode != YG_EQ_EXACT) {
-        yg_set_error("large linear model: MRW / two-level delayed acceptance with exact equality only");
+    if (pb->proposal != YG_PROPOSAL_MRW || e->cfg.adaptive || e->cfg.eq_mode != YG_EQ_EXACT || e->cfg.aem || nl > 2) {
+        yg_set_error("large linear model (dim > %d or data_dim > %d): MRW / two-level delayed acceptance with exact "
+                     "equality only (no adaptive proposal, adaptive error model or third level)", YG_MAX_DIM, YG_MAX_DATA_DIM);
         return YG_ERR_UNSUPPORTED;
     }
+    for (int l = 0; l < nl; l++)
+        if (pb->level[l].tempered) {
+            yg_set_error("large linear model: tempered levels are not implemented");
+            return YG_ERR_UNSUPPORTED;
+        }
     if (!is_diagonal(pb->prop_L, d)) {
         yg_set_error("large linear model: the proposal factor must be diagonal");
         return YG_ERR_UNSUPPORTED;
@@ -227,12 +234,17 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
         yg_set_error("adaptive Metropolis is limited to dim <= %d", YG_MAX_DIM);
         return YG_ERR_UNSUPPORTED;
     }
-    if (cfg->n_levels != 1 && cfg->n_levels != 2) {
-        yg_set_error("n_levels=%d: only MRW (1) and two-level delayed acceptance (2) exist on the device",
-                     cfg->n_levels);
+    if (cfg->n_levels < 1 || cfg->n_levels > YG_MAX_LEVELS) {
+        yg_set_error("n_levels=%d: MRW (1), two-level delayed acceptance (2) and MLDA with two surrogates (3) "
+                     "exist on the device", cfg->n_levels);
         return YG_ERR_UNSUPPORTED;
     }
-    if (cfg->n_levels == 2 && cfg->sub_chain_length < 1) {
+    if (cfg->n_levels == 3 && (cfg->model == YG_MODEL_LV_RK4 || cfg->aem || cfg->dim > YG_MAX_DIM)) {
+        yg_set_error("three levels: Gaussian targets and the linear model (dim <= %d) only, no adaptive error model",
+                     YG_MAX_DIM);
+        return YG_ERR_UNSUPPORTED;
+    }
+    if (cfg->n_levels >= 2 && cfg->sub_chain_length < 1) {
         yg_set_error("sub_chain_length must be >= 1");
         return YG_ERR_INVALID;
     }
@@ -244,9 +256,13 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
         yg_set_error("the Lotka-Volterra model has two parameters (dim=%d)", cfg->dim);
         return YG_ERR_INVALID;
     }
-    if (cfg->adaptive && (cfg->n_levels != 1 || cfg->model == YG_MODEL_LV_RK4 || cfg->dim < 2)) {
-        yg_set_error("adaptive Metropolis: single level, dim >= 2, Gaussian/linear models only");
-        return YG_ERR_UNSUPPORTED;   // dim == 1: chain/adaptive.py:41-43 refuses scalar chains too
+    if (cfg->adaptive && cfg->dim < 2) {
+        yg_set_error("Adaptivity not implemented for scalar chains.");      // chain/adaptive.py:41-43
+        return YG_ERR_UNSUPPORTED;
+    }
+    if (cfg->adaptive && (cfg->am_idle_steps < 0 || cfg->am_collection_steps < 0 || cfg->am_refresh < 0)) {
+        yg_set_error("adaptive Metropolis: idle / collection steps and the refresh interval must be >= 0");
+        return YG_ERR_INVALID;
     }
     if (cfg->aem) {
         if (cfg->n_levels != 2 || cfg->model != YG_MODEL_LINEAR || cfg->adaptive || cfg->dim > YG_MAX_DIM) {
@@ -275,10 +291,14 @@ extern "C" int yg_create(const yg_config *cfg, yg_ensemble **out)
         return YG_ERR_INVALID;
     }
     e->cfg = *cfg;
-    YG_CUDA_CHECK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+    if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess) {
+        yg_set_error("cudaDeviceGetAttribute(multiProcessorCount) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return YG_ERR_CUDA;
+    }
     const size_t n = (size_t)cfg->n_chains, d = (size_t)cfg->dim;
     int rc = YG_OK;
-    if ((rc = dev_alloc(&e->theta, d * n)) || (rc = dev_alloc(&e->logpost, 2 * n)) ||
+    if ((rc = dev_alloc(&e->theta, d * n)) || (rc = dev_alloc(&e->logpost, YG_MAX_LEVELS * n)) ||
         (rc = dev_alloc(&e->w_mean, d * n)) || (rc = dev_alloc(&e->w_m2, (cfg->dim > YG_MAX_DIM ? d : d * d) * n)) ||
         (rc = dev_alloc(&e->n_accept, n)) || (rc = dev_alloc(&e->counters, 8)) ||
         (rc = dev_alloc(&e->pool_partials, (size_t)POOL_PARTS * (size_t)yg_pooled_len(std::min(cfg->dim, YG_MAX_DIM))))) {
@@ -385,7 +405,7 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
     h->model = model;
     h->dim = d;
     h->n_levels = nl;
-    h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
+    h->J = nl >= 2 ? e->cfg.sub_chain_length : 1;
     h->eq_mode = e->cfg.eq_mode;
     h->tail_len = (int32_t)tail_len;
     h->proposal = pb->proposal;
@@ -414,6 +434,14 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
         }
         D.n_data = L.n_data;
         D.data_dim = L.data_dim;
+        D.tempering = 1.0;
+        if (L.tempered) {
+            if (!(L.tempering >= 0.0 && L.tempering <= 1.0)) {       // tmlda.py:24-29
+                yg_set_error("Invalid tempering parameter at index %d: %g (must be in [0, 1]).", l, L.tempering);
+                return YG_ERR_INVALID;
+            }
+            D.tempering = L.tempering;
+        }
         copy_mat(D.noise_prec, L.noise_prec, L.data_dim, L.data_dim);
         copy_mat(D.prior_mean, L.prior_mean, 1, d);
         copy_mat(D.prior_prec, L.prior_prec, d, d);
@@ -433,13 +461,6 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
             off += (size_t)L.n_data * 2;
         }
     }
-    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-    if (e->d_problem) cudaFree(e->d_problem);
-    e->d_problem = nullptr;
-    YG_CUDA_CHECK(cudaMalloc((void **)&e->d_problem, blob.size()));
-    YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    e->h_problem.swap(blob);
-    e->problem_set = true;
     if (e->cfg.aem) {
         const yg_level &Lc = pb->level[0], &Lf = pb->level[1];
         if (Lc.data_dim != Lf.data_dim || pb->proposal != YG_PROPOSAL_MRW) {
@@ -453,7 +474,16 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
                     yg_set_error("Currently, AEM is only implemented for independent measurement noise.");
                     return YG_ERR_UNSUPPORTED;
                 }
-        const size_t n = (size_t)e->cfg.n_chains, dd = (size_t)Lc.data_dim;
+    }
+    YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->problem_set = false;                     // stays false if anything below fails
+    if (e->d_problem) cudaFree(e->d_problem);
+    e->d_problem = nullptr;
+    YG_CUDA_CHECK(cudaMalloc((void **)&e->d_problem, blob.size()));
+    YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    e->h_problem.swap(blob);
+    if (e->cfg.aem) {
+        const size_t n = (size_t)e->cfg.n_chains, dd = (size_t)pb->level[0].data_dim;
         cudaFree(e->aem_n); cudaFree(e->aem_mean); cudaFree(e->aem_m2); cudaFree(e->aem_cache);
         e->aem_n = nullptr; e->aem_mean = e->aem_m2 = e->aem_cache = nullptr;
         e->aem_data_dim = (int)dd;
@@ -461,10 +491,11 @@ extern "C" int yg_set_problem(yg_ensemble *e, const yg_problem *pb)
             (rc = dev_alloc(&e->aem_m2, dd * n)) || (rc = dev_alloc(&e->aem_cache, (size_t)(3 * (d + 1) + 1) * n)))
             return rc;
     }
+    e->problem_set = true;
     return YG_OK;
 }
 
-extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stream)
+extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, int32_t flags, void *stream)
 {
     int rc = check_handle(e, true, false);
     if (rc) return rc;
@@ -474,20 +505,27 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.n_chains, d = (size_t)e->cfg.dim;
+    // a handle that never held a state has nothing to keep
+    const bool keep_diag = (flags & YG_KEEP_DIAGNOSTICS) && e->state_set;
+    const bool keep_adapt = (flags & YG_KEEP_ADAPTATION) && e->state_set;
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     YG_CUDA_CHECK(cudaMemcpyAsync(e->theta, theta0_dev, sizeof(double) * d * n, cudaMemcpyDeviceToDevice, st));
-    YG_CUDA_CHECK(cudaMemsetAsync(e->w_mean, 0, sizeof(double) * d * n, st));
-    YG_CUDA_CHECK(cudaMemsetAsync(e->w_m2, 0, sizeof(double) * (d > YG_MAX_DIM ? d : d * d) * n, st));
-    YG_CUDA_CHECK(cudaMemsetAsync(e->n_accept, 0, sizeof(unsigned long long) * n, st));
-    YG_CUDA_CHECK(cudaMemsetAsync(e->counters, 0, sizeof(unsigned long long) * 8, st));
-    if (e->cfg.adaptive) {
+    if (!keep_diag) {
+        YG_CUDA_CHECK(cudaMemsetAsync(e->w_mean, 0, sizeof(double) * d * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->w_m2, 0, sizeof(double) * (d > YG_MAX_DIM ? d : d * d) * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->n_accept, 0, sizeof(unsigned long long) * n, st));
+        YG_CUDA_CHECK(cudaMemsetAsync(e->counters, 0, sizeof(unsigned long long) * 8, st));
+        e->welford_n = 0;
+    }
+    if (e->cfg.adaptive && !keep_adapt) {
         YG_CUDA_CHECK(cudaMemsetAsync(e->am_mean, 0, sizeof(double) * d * n, st));
         YG_CUDA_CHECK(cudaMemsetAsync(e->am_m2, 0, sizeof(double) * d * d * n, st));
         broadcast_L_kernel<<<(int)std::min<size_t>((n + 127) / 128, 2048), 128, 0, st>>>(e->d_problem, e->prop_L,
                                                                                       (int64_t)n);
         YG_CUDA_CHECK(cudaGetLastError());
+        e->am_steps = 0;
     }
-    if (e->cfg.aem) {       // empty cache, no error realisations yet
+    if (e->cfg.aem && !keep_adapt) {       // empty cache, no error realisations yet
         YG_CUDA_CHECK(cudaMemsetAsync(e->aem_n, 0, sizeof(unsigned long long) * n, st));
         YG_CUDA_CHECK(cudaMemsetAsync(e->aem_mean, 0, sizeof(double) * (size_t)e->aem_data_dim * n, st));
         YG_CUDA_CHECK(cudaMemsetAsync(e->aem_m2, 0, sizeof(double) * (size_t)e->aem_data_dim * n, st));
@@ -498,9 +536,21 @@ extern "C" int yg_set_state(yg_ensemble *e, const double *theta0_dev, void *stre
                     : yg_launch_logpost(e, l, e->theta, (int64_t)n, e->logpost + (size_t)l * n, st);
         if (rc) return rc;
     }
-    e->step_index = 0;
-    e->welford_n = 0;
+    // e->step_index (the Philox stream position) is deliberately left alone: the reference's numpy
+    // generator keeps advancing across run() calls, and so does this stream (yg_seek repositions it)
     e->state_set = true;
+    return YG_OK;
+}
+
+extern "C" int yg_seek(yg_ensemble *e, int64_t step_index)
+{
+    int rc = check_handle(e, false, false);
+    if (rc) return rc;
+    if (step_index < 0) {
+        yg_set_error("yg_seek: step_index must be >= 0");
+        return YG_ERR_INVALID;
+    }
+    e->step_index = step_index;
     return YG_OK;
 }
 
@@ -598,6 +648,7 @@ extern "C" int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin, const yg_ou
     if (rc) return rc;
     e->step_index += n_steps;
     e->welford_n += n_steps;
+    if (e->cfg.adaptive) e->am_steps += n_steps;
     return YG_OK;
 }
 
@@ -644,7 +695,8 @@ extern "C" int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream)
     return YG_OK;
 }
 
-extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n, void *stream)
+extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n,
+                             int64_t am_steps, void *stream)
 {
     int rc = check_handle(e, true, false);
     if (rc) return rc;
@@ -676,6 +728,7 @@ extern "C" int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_i
     }
     e->step_index = step_index;
     e->welford_n = welford_n;
+    e->am_steps = am_steps;
     e->state_set = true;
     return YG_OK;
 }
@@ -695,6 +748,8 @@ extern "C" int yg_get_counters(yg_ensemble *e, int64_t *out_host, void *stream)
     out_host[3] = (int64_t)c[2];
     out_host[4] = (int64_t)c[3];
     out_host[5] = e->welford_n;
+    out_host[6] = e->am_steps;
+    out_host[7] = (int64_t)c[4];
     return YG_OK;
 }
 

@@ -26,6 +26,8 @@ struct DevLevel {
     double G[YG_MAX_DATA_DIM * YG_MAX_DIM];
     double b[YG_MAX_DATA_DIM];
     double alpha, gamma, T;
+    double tempering;      // logL multiplier: 1 unless the level is a TemperedUnnormalisedPosterior (target.py:25-43)
+    double _padt;
     int32_t rk4_steps, n_data, data_dim;
     int32_t data_off;      // offsets (in doubles) into DevProblem::tail
     int32_t design_off;
@@ -39,7 +41,7 @@ struct DevProblemHeader {
     double pcn_a, pcn_b;       // sqrt(1 - 2h), sqrt(2h)   (pcn.py:30-35)
     double pcn_mean[YG_MAX_DIM];
     double prop_L[YG_MAX_DIM * YG_MAX_DIM];
-    DevLevel lvl[2];
+    DevLevel lvl[YG_MAX_LEVELS];
     // followed by double tail[tail_len]: per level data[n_data*data_dim], design[n_data*2]
 };
 static_assert(sizeof(DevLevel) % 16 == 0, "DevLevel must keep 16-byte alignment");

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(IAT_THREADS) iat_kernel(const double *samples,
     const int tid = threadIdx.x;
     for (int64_t chain = blockIdx.x; chain < nc; chain += gridDim.x) {
         long long best = 0;
+        bool degenerate = false;         // block-uniform: derived from block_sum4 results only
         const int n_series = (method == 0) ? 1 : d;
         for (int k = 0; k < n_series; k++) {
             __syncthreads();
@@ -88,14 +89,21 @@ __global__ void __launch_bounds__(IAT_THREADS) iat_kernel(const double *samples,
                         if (i + M0 + l < ns) v[l] = fma(xi, x[i + M0 + l], v[l]);
                 }
                 block_sum4(v, red);
-                if (M0 == 0) acf0 = v[0];
+                if (M0 == 0) {
+                    acf0 = v[0];
+                    // A constant (stuck / never accepted) or non-finite series has no autocorrelation function:
+                    // 0/0 in the reference (autocorrelation.py:26-29; it fails on the NaNs).  A batched call cannot
+                    // raise per chain, so such a chain reports IAT = n_samples and ESS = 0 -- never a full ESS.
+                    if (!(acf0 > 0.0) || !isfinite(acf0)) { degenerate = true; break; }
+                }
 #pragma unroll
                 for (int l = 0; l < IAT_LAGS; l++) {
                     const int64_t M = M0 + l;
                     if (!done && M < ns) {
                         cum += v[l] / acf0;
                         const double tau = 2.0 * cum - 1.0;
-                        if (!((double)M < sokal * tau)) {
+                        if (!isfinite(tau)) { degenerate = true; done = true; }
+                        else if (!((double)M < sokal * tau)) {
                             result = (long long)rint(tau);
                             done = true;
                         }
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(IAT_THREADS) iat_kernel(const double *samples,
             if (k == 0 || result > best) best = result;
         }
         if (tid == 0) {
-            if (iat_out) iat_out[chain] = best;
-            if (ess_out) ess_out[chain] = ns / (best > 0 ? best : 1);
+            if (iat_out) iat_out[chain] = degenerate ? (long long)ns : best;
+            if (ess_out) ess_out[chain] = degenerate ? 0 : ns / (best > 0 ? best : 1);
         }
     }
 }

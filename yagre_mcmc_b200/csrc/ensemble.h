@@ -11,9 +11,10 @@ struct RunArgs {
     int64_t n_chains, chain_offset;
     uint64_t seed;
     int64_t step0, n_steps, welford_n0;
+    int64_t am_t0;                  // transitions since the adaptation state was reset (base of the AM update index)
     // per-chain state, SoA, chain index fastest
     double *theta;                  // [d, n]
-    double *logpost;                // [2, n]
+    double *logpost;                // [n_levels, n]
     unsigned long long *n_accept;   // [n]
     double *w_mean;                 // [d, n]
     double *w_m2;                   // [d*d, n]
@@ -41,7 +42,7 @@ struct RunArgs {
     // three vector-register sources issues slower than one with two + a constant operand).
     double lv_h[2];
     LvStepConsts lv_k[2];
-    // [0] transitions [1] accepted [2] level-0 evals [3] level-1 evals
+    // [0] transitions [1] accepted [2] level-0 evals [3] target-level evals [4] level-1 evals of three levels
     unsigned long long *counters;
 };
 
@@ -59,7 +60,7 @@ struct yg_ensemble {
     int aem_data_dim = 0;
     unsigned long long *n_accept = nullptr, *counters = nullptr;
     double *pool_partials = nullptr;   // [POOL_PARTS][yg_pooled_len(d)] scratch of yg_pooled_stats
-    int64_t step_index = 0, welford_n = 0;
+    int64_t step_index = 0, welford_n = 0, am_steps = 0;
     int last_grid = 0, last_block = 0, last_smem = 0;
     int64_t launches = 0;
 };

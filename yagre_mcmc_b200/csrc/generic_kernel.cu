@@ -18,9 +18,9 @@ int yg_launch_generic(yg_ensemble *e, const RunArgs &a, bool, cudaStream_t st)
 {
     const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
     const int cd = cap_of(hp->dim);
-    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim)));
+    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, std::max(hp->lvl[1].data_dim, hp->lvl[2].data_dim))));
     int rc = YG_ERR_UNSUPPORTED;
-    if (hp->dim <= 8 && std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim) <= 8) {
+    if (hp->dim <= 8 && std::max(hp->lvl[0].data_dim, std::max(hp->lvl[1].data_dim, hp->lvl[2].data_dim)) <= 8) {
 #ifdef YG_DEV_22
         if (cd == 2) rc = yg_launch_generic_d2(e, a, st, cdd);
 #else
@@ -36,9 +36,9 @@ int yg_launch_logpost(yg_ensemble *e, int level, const double *theta, int64_t n,
 {
     const DevProblemHeader *hp = reinterpret_cast<const DevProblemHeader *>(e->h_problem.data());
     const int cd = cap_of(hp->dim);
-    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim)));
+    const int cdd = cap_of(std::max(1, std::max(hp->lvl[0].data_dim, std::max(hp->lvl[1].data_dim, hp->lvl[2].data_dim))));
     int rc = YG_ERR_UNSUPPORTED;
-    if (hp->dim <= 8 && std::max(hp->lvl[0].data_dim, hp->lvl[1].data_dim) <= 8) {
+    if (hp->dim <= 8 && std::max(hp->lvl[0].data_dim, std::max(hp->lvl[1].data_dim, hp->lvl[2].data_dim)) <= 8) {
 #ifdef YG_DEV_22
         if (cd == 2) rc = yg_launch_logpost_d2(e, level, theta, n, out, st, cdd);
 #else

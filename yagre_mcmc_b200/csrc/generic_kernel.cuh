@@ -110,7 +110,8 @@ YG_DEVFN double logpost_any(const DevProblemHeader *pb, int lvl, const double (&
             return quad_form<2>(Lv.noise_prec, 2, r, 2);
         });
     }
-    const double logL = -0.5 * sum;
+    // tempering = 1 (an exact identity) unless the level is a TemperedUnnormalisedPosterior (target.py:40-43)
+    const double logL = __dmul_rn(Lv.tempering, -0.5 * sum);
 #pragma unroll
     for (int i = 0; i < D; i++) x[i] = (i < d) ? t[i] - Lv.prior_mean[i] : 0.0;
     return logL + (-0.5 * quad_form<D>(Lv.prior_prec, d, x, d));
@@ -141,27 +142,33 @@ __global__ void logpost_kernel(const DevProblemHeader *gpb, uint32_t bytes, int 
 }
 
 // In-register Cholesky of the d x d leading block; returns false if not positive definite.
+// Operation order of LAPACK's unblocked dpotf2 (what scipy.linalg.cholesky runs for the reference's
+// DenseCovarianceMatrix, statistics/covariance.py:78): a_jj = sqrt(c_jj - dot), and the column below is
+// scaled by the RECIPROCAL 1 / a_jj (DSCAL), not divided.  Unfused, so that the factor equals the host's
+// bit for bit for d <= 3 (tests/golden/am_*.npz).
 template <int D>
 YG_DEVFN bool cholesky_lower(const double (&C)[D][D], double (&L)[D][D], int d)
 {
 #pragma unroll
     for (int j = 0; j < D; j++) {
         if (j < d) {
-            double s = C[j][j];
+            double dot = 0.0;
 #pragma unroll
             for (int k = 0; k < D; k++)
-                if (k < j) s -= L[j][k] * L[j][k];
+                if (k < j) dot = __dadd_rn(dot, __dmul_rn(L[j][k], L[j][k]));
+            const double s = __dsub_rn(C[j][j], dot);
             if (!(s > 0.0)) return false;
             const double ljj = sqrt(s);
             L[j][j] = ljj;
+            const double rcp = 1.0 / ljj;
 #pragma unroll
             for (int i = 0; i < D; i++) {
                 if (i > j && i < d) {
-                    double v = C[i][j];
+                    double dt = 0.0;
 #pragma unroll
                     for (int k = 0; k < D; k++)
-                        if (k < j) v -= L[i][k] * L[j][k];
-                    L[i][j] = v / ljj;
+                        if (k < j) dt = __dadd_rn(dt, __dmul_rn(L[i][k], L[j][k]));
+                    L[i][j] = __dmul_rn(__dsub_rn(C[i][j], dt), rcp);
                 }
                 if (i < j) L[i][j] = 0.0;
             }
@@ -198,11 +205,15 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
     const DevProblemHeader *pb = reinterpret_cast<const DevProblemHeader *>(smem_raw);
     const int d = pb->dim;
     const int J = TWO_LEVEL ? pb->J : 1;
-    const int n_lvl = TWO_LEVEL ? 2 : 1;
+    // TWO_LEVEL covers delayed acceptance with one surrogate and MLDA with two surrogates as the reference runs
+    // it (mlda.py:12-43,60-71,112-117): sub-chain on level 0, screen with the finest surrogate (level 1) against
+    // the target (level 2)
+    const int n_lvl = TWO_LEVEL ? pb->n_levels : 1;
+    const bool three = TWO_LEVEL && n_lvl == 3;
     const int64_t N = a.n_chains;
     const bool isclose_eq = pb->eq_mode == YG_EQ_ISCLOSE;
     const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
-    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_ev2 = 0ull, cnt_tr = 0ull;
 
     const int ws_lane = threadIdx.x & 31;
     const int ws_per_step = TWO_LEVEL ? J + 1 : 1;       // ring entries per transition
@@ -267,6 +278,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
             am_m[i] = (a.adaptive && i < d) ? a.am_mean[i * N + g] : 0.0;
         }
         double lp0 = a.logpost[g], lp1 = TWO_LEVEL ? a.logpost[N + g] : 0.0;
+        double lp2 = three ? a.logpost[2 * N + g] : 0.0;
         unsigned long long nacc = a.n_accept[g];
 
         auto equal = [&](const double (&p)[D], const double (&s)[D]) {
@@ -325,6 +337,44 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
             }
         };
 
+        // ---- adaptive Metropolis: AdaptiveMRWProposal.set_state -> update() (adaptive.py:55-60) runs before
+        // every proposal of the MRW chain it drives, with that chain's current state x (the sub-chain state in
+        // the two-level case); t_idx = number of earlier updates.  Recurrence: DESIGN.md section 5, arithmetic
+        // pinned to oracle/ref_harness.py HaarioAdaptiveCovariance (unfused, numpy order).
+        auto am_update = [&](const double (&x)[D], const int64_t t_idx) {
+            if (t_idx < a.am_idle) return;
+            const int64_t n_am = t_idx - a.am_idle + 1;
+            double dl[D], e[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                dl[i] = __dsub_rn(x[i], am_m[i]);
+                am_m[i] = __dadd_rn(am_m[i], dl[i] / (double)n_am);
+                e[i] = __dsub_rn(x[i], am_m[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++)
+#pragma unroll
+                for (int j = 0; j < D; j++) am_2[i][j] = __dadd_rn(am_2[i][j], __dmul_rn(dl[i], e[j]));
+            if (n_am >= a.am_collect && n_am >= 2 && (a.am_refresh == 1 || ((n_am - a.am_collect) % a.am_refresh) == 0)) {
+                double Cm[D][D], Ln[D][D];
+#pragma unroll
+                for (int i = 0; i < D; i++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) {
+                        // symmetrised sample covariance, C = s (Cov + eps I)
+                        const double cov = __dmul_rn(0.5, __dadd_rn(am_2[i][j], am_2[j][i])) / (double)(n_am - 1);
+                        Cm[i][j] = __dmul_rn(a.am_scale, (i == j) ? __dadd_rn(cov, a.am_eps) : cov);
+                        Ln[i][j] = 0.0;
+                    }
+                if (cholesky_lower<D>(Cm, Ln, d)) {
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+#pragma unroll
+                        for (int j = 0; j < D; j++) L[i][j] = Ln[i][j];
+                }
+            }
+        };
+
         int64_t thin_left = a.thin, thin_out = 0;
         for (int64_t n = 0; n < a.n_steps; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
@@ -343,45 +393,10 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
 #pragma unroll
                     for (int j = 0; j < D; j++) w2[i][j] += dl[i] * e[j];
             }
-            // ---- adaptive Metropolis: update() before the proposal (adaptive.py:55-60) ----
-            if (a.adaptive) {
-                const int64_t t_idx = a.step0 + n;
-                if (t_idx >= a.am_idle) {
-                    const int64_t n_am = t_idx - a.am_idle + 1;
-                    double dl[D], e[D];
-#pragma unroll
-                    for (int i = 0; i < D; i++) {
-                        dl[i] = th[i] - am_m[i];
-                        am_m[i] += dl[i] / (double)n_am;
-                        e[i] = th[i] - am_m[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < D; i++)
-#pragma unroll
-                        for (int j = 0; j < D; j++) am_2[i][j] += dl[i] * e[j];
-                    if (n_am >= a.am_collect && n_am >= 2 && (a.am_refresh == 1 || ((n_am - a.am_collect) % a.am_refresh) == 0)) {
-                        double Cm[D][D], Ln[D][D];
-#pragma unroll
-                        for (int i = 0; i < D; i++)
-#pragma unroll
-                            for (int j = 0; j < D; j++) {
-                                // symmetrised sample covariance, C = s (Cov + eps I)
-                                const double cov = 0.5 * (am_2[i][j] + am_2[j][i]) / (double)(n_am - 1);
-                                Cm[i][j] = a.am_scale * (cov + ((i == j) ? a.am_eps : 0.0));
-                                Ln[i][j] = 0.0;
-                            }
-                        if (cholesky_lower<D>(Cm, Ln, d)) {
-#pragma unroll
-                            for (int i = 0; i < D; i++)
-#pragma unroll
-                                for (int j = 0; j < D; j++) L[i][j] = Ln[i][j];
-                        }
-                    }
-                }
-            }
             bool accepted = false;
             if (!TWO_LEVEL) {
                 double p[D];
+                if (a.adaptive) am_update(th, a.am_t0 + n);
                 if (WS) ws_fetch();
                 propose(th, n, 0, step, p);
                 if (!equal(p, th)) {                                    // metropolisHastings.py:60-61
@@ -407,6 +422,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
                 for (int i = 0; i < D; i++) s[i] = th[i];
                 double lps = lp0;
                 for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
+                    if (a.adaptive) am_update(s, (a.am_t0 + n) * J + j);
                     if (WS) ws_fetch();
                     propose(s, n, j, step, p);
                     if (equal(p, s)) continue;
@@ -428,8 +444,12 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
                 }
                 if (WS) ws_fetch();
                 if (!equal(s, th)) {
-                    const double lpf_s = logpost_any<D, DD>(pb, 1, s);
-                    cnt_ev1++;
+                    // levels above the sub-chain's: one (the target) or two (finest surrogate, target)
+                    double lpm_s = 0.0, lpf_s = 0.0;
+                    for (int lv = 1; lv < n_lvl; lv++) {
+                        const double v = logpost_any<D, DD>(pb, lv, s);
+                        if (lv == n_lvl - 1) { lpf_s = v; cnt_ev1++; } else { lpm_s = v; cnt_ev2++; }
+                    }
                     double u;
                     if (WS) u = ws_u;
                     else if (a.noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + g];
@@ -437,12 +457,14 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
                         u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
                         if (a.noise_mode == YG_NOISE_RECORD) a.u_f[n * N + g] = u;
                     }
-                    const double delta = lpf_s + lp0 - lps - lp1;      // mlda.py:148-152, this order
+                    // mlda.py:148-152, this order: pi_f(p) + pi_c(s) - pi_c(p) - pi_f(s); with two surrogates
+                    // pi_c is the FINEST surrogate although the sub-chain ran on the base one (mlda.py:130,146-154)
+                    const double delta = three ? lpf_s + lp1 - lpm_s - lp2 : lpf_s + lp0 - lps - lp1;
                     if (accept_rule(delta, u)) {
 #pragma unroll
                         for (int i = 0; i < D; i++) th[i] = s[i];
                         lp0 = lps;
-                        lp1 = lpf_s;
+                        if (three) { lp1 = lpm_s; lp2 = lpf_s; } else lp1 = lpf_s;
                         accepted = true;
                     }
                 }
@@ -461,6 +483,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
                 if (a.lp_out) {
                     a.lp_out[(o * n_lvl) * N + g] = lp0;
                     if (TWO_LEVEL) a.lp_out[(o * n_lvl + 1) * N + g] = lp1;
+                    if (three) a.lp_out[(o * n_lvl + 2) * N + g] = lp2;
                 }
             }
         }
@@ -485,17 +508,18 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
         }
         a.logpost[g] = lp0;
         if (TWO_LEVEL) a.logpost[N + g] = lp1;
+        if (three) a.logpost[2 * N + g] = lp2;
         a.n_accept[g] = nacc;
     }
     // ---- counters: warp-shuffle reduction, one atomic per warp ------------------------------
-    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+    unsigned long long v[5] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_ev2};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-#pragma unroll
+    for (int k = 0; k < 5; k++) {
         if (WS) {                                   // exited lanes (chains beyond N, producers) cannot shuffle
             if (v[k]) atomicAdd(&a.counters[k], v[k]);
             continue;
         }
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
     }
@@ -894,11 +918,11 @@ int launch_generic_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     const int64_t want = (a.n_chains + threads - 1) / threads;
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * 16));
     size_t smem = (e->h_problem.size() + 15) & ~size_t(15);
-    auto kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true, false> : generic_mh_kernel<D, DD, false, false>;
+    auto kern = e->cfg.n_levels >= 2 ? generic_mh_kernel<D, DD, true, false> : generic_mh_kernel<D, DD, false, false>;
     // small ensembles with Philox noise: warp-specialised variant (see WS above); the parity modes
     // (injected / recorded noise) stay on the plain kernel, which the WS variant equals bit for bit
     if (D == 2 && a.noise_mode == YG_NOISE_PHILOX && a.n_chains <= WS_MAX_CHAINS && a.n_steps > 0) {
-        kern = e->cfg.n_levels == 2 ? generic_mh_kernel<D, DD, true, D == 2> : generic_mh_kernel<D, DD, false, D == 2>;
+        kern = e->cfg.n_levels >= 2 ? generic_mh_kernel<D, DD, true, D == 2> : generic_mh_kernel<D, DD, false, D == 2>;
         threads = WS_THREADS;
         grid = (int)((a.n_chains + 31) / 32);
         smem += sizeof(double) * WS_RING * 96 + sizeof(unsigned long long) * (WS_RING + 1);

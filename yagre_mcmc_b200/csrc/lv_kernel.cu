@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     auto log_post_from_q = [&](int lvl, int c, double t0, double t1) {
         const int nD = pb->lvl[lvl].n_data;
         const double logL = -0.5 * (nD <= 128 ? np_sum_le128(q + c, nD, cmax) : np_pairwise_sum(q + c, nD, cmax));
-        return logL + log_prior(lvl, t0, t1);
+        // tempering = 1 (exact identity) unless the level is a TemperedUnnormalisedPosterior (target.py:40-43)
+        return __dmul_rn(pb->lvl[lvl].tempering, logL) + log_prior(lvl, t0, t1);
     };
 
     // noise: injected arrays are indexed by (step, sub-step), never by call count.  draw_z /
@@ -267,6 +268,43 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
             if (a.noise_mode == YG_NOISE_RECORD) arr[i] = u;
         }
         nz[2 * cmax + c] = u;
+    };
+
+    // Adaptive Metropolis (chain/adaptive.py:55-60: update() before every proposal of the MRW chain it drives,
+    // with that chain's current state = the sub-chain state s; t = number of earlier updates).  Per-chain
+    // moments and proposal factor stay in (L2-resident) global memory: they are touched once per proposal by the
+    // chain's owner only, and the shared-memory budget belongs to the evaluation phases.  Recurrence of
+    // DESIGN.md section 5 in the unfused numpy order of oracle/ref_harness.py HaarioAdaptiveCovariance; the
+    // 2 x 2 Cholesky in LAPACK dpotf2's order (reciprocal scaling), like the reference's DenseCovarianceMatrix.
+    auto am_update = [&](const int64_t g, const int64_t t, const double x0, const double x1, double &l00, double &l10,
+                         double &l11) {
+        l00 = a.prop_L[g]; l10 = a.prop_L[2 * N + g]; l11 = a.prop_L[3 * N + g];
+        if (t < a.am_idle) return;
+        const int64_t n_am = t - a.am_idle + 1;
+        double m0 = a.am_mean[g], m1 = a.am_mean[N + g];
+        double v00 = a.am_m2[g], v01 = a.am_m2[N + g], v10 = a.am_m2[2 * N + g], v11 = a.am_m2[3 * N + g];
+        const double dn = (double)n_am;
+        const double d0 = __dsub_rn(x0, m0), d1 = __dsub_rn(x1, m1);
+        m0 = __dadd_rn(m0, d0 / dn); m1 = __dadd_rn(m1, d1 / dn);
+        const double e0 = __dsub_rn(x0, m0), e1 = __dsub_rn(x1, m1);
+        v00 = __dadd_rn(v00, __dmul_rn(d0, e0)); v01 = __dadd_rn(v01, __dmul_rn(d0, e1));
+        v10 = __dadd_rn(v10, __dmul_rn(d1, e0)); v11 = __dadd_rn(v11, __dmul_rn(d1, e1));
+        a.am_mean[g] = m0; a.am_mean[N + g] = m1;
+        a.am_m2[g] = v00; a.am_m2[N + g] = v01; a.am_m2[2 * N + g] = v10; a.am_m2[3 * N + g] = v11;
+        if (n_am >= a.am_collect && n_am >= 2 && (a.am_refresh == 1 || ((n_am - a.am_collect) % a.am_refresh) == 0)) {
+            const double dm = (double)(n_am - 1);
+            const double c00 = __dmul_rn(a.am_scale, __dadd_rn(__dmul_rn(0.5, __dadd_rn(v00, v00)) / dm, a.am_eps));
+            const double c10 = __dmul_rn(a.am_scale, __dmul_rn(0.5, __dadd_rn(v10, v01)) / dm);
+            const double c11 = __dmul_rn(a.am_scale, __dadd_rn(__dmul_rn(0.5, __dadd_rn(v11, v11)) / dm, a.am_eps));
+            if (c00 > 0.0) {
+                const double n00 = sqrt(c00), n10 = __dmul_rn(c10, 1.0 / n00);
+                const double s11 = __dsub_rn(c11, __dmul_rn(n10, n10));
+                if (s11 > 0.0) {
+                    l00 = n00; l10 = n10; l11 = sqrt(s11);
+                    a.prop_L[g] = l00; a.prop_L[2 * N + g] = l10; a.prop_L[3 * N + g] = l11;
+                }
+            }
+        }
     };
 
 #ifdef YG_TIMERS
@@ -340,11 +378,13 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                     }
                     CH(S0, c) = s0; CH(S1, c) = s1; CH(LPS, c) = lps;
                     if (j < J) {
+                        double l00 = L00, l10 = L10, l11 = L11;
+                        if (a.adaptive) am_update(cb + c, (a.am_t0 + n) * J + j, s0, s1, l00, l10, l11);
                         // propose sub-step j: p = s + L z  (gaussian.py:61-66), unfused like numpy
                         const double z0 = nz[c], z1 = nz[cmax + c];          // z(n, j)
-                        const double lz0 = __dmul_rn(L00, z0);
-                        const double lz1 = (L10 != 0.0) ? __dadd_rn(__dmul_rn(L10, z0), __dmul_rn(L11, z1))
-                                                        : __dmul_rn(L11, z1);
+                        const double lz0 = __dmul_rn(l00, z0);
+                        const double lz1 = (l10 != 0.0) ? __dadd_rn(__dmul_rn(l10, z0), __dmul_rn(l11, z1))
+                                                        : __dmul_rn(l11, z1);
                         double p0, p1;
                         if (pcn) {    // pcn.py:30-35: sqrt(1-t) * state + sqrt(t) * (mean + L z)
                             p0 = __dadd_rn(__dmul_rn(pb->pcn_a, s0), __dmul_rn(pb->pcn_b, __dadd_rn(pb->pcn_mean[0], lz0)));

@@ -27,11 +27,15 @@ class LoweredProblem:
     """The plain-array form of a (hierarchy of) Bayesian model(s) + proposal, i.e.
     what ChainBuilder.build_method() (reference chain/builder.py:72-83) boils down to.
 
-    meta:   model ('gauss'|'linear'|'lv'), dim, levels (1|2), J, eq ('exact'|'isclose'),
+    meta:   model ('gauss'|'linear'|'lv'), dim, levels (1|2|3), J, eq ('exact'|'isclose'),
             proposal ('mrw'|'pcn') and pcn_step for pCN (prop_L is then the prior's factor and the
             level's prior_prec is zero: the pCN target is the likelihood alone, pcn.py:52-57)
     arrays: prop_L[d,d] and per level l: L{l}_g_mean/g_prec/g_logconst (gauss),
-            L{l}_data/noise_prec/prior_mean/prior_prec (+ L{l}_G/b | L{l}_design/lv=[alpha,gamma,T,N])
+            L{l}_data/noise_prec/prior_mean/prior_prec (+ L{l}_G/b | L{l}_design/lv=[alpha,gamma,T,N]),
+            optionally L{l}_tempering (TemperedUnnormalisedPosterior, chain/target.py:25-43)
+    levels == 3 is MLDA with two surrogates as the reference runs it (mlda.py:12-43,60-71,112-117): level 0
+    drives the MRW sub-chain of J = subChainLengths[1] steps, level 1 (the finest surrogate) screens, level 2
+    is the target.
     """
 
     def __init__(self, meta, arrays):
@@ -49,7 +53,7 @@ class LoweredProblem:
                 f"model {self.model!r} has no device implementation; the backend accepts Gaussian targets, "
                 "linear models and the Lotka-Volterra RK4 model only (no CPU fallback)")
         self.arrays = {k: _f64(v) for k, v in arrays.items()
-                       if k in ('prop_L', 'pcn_mean') or k.startswith('L0_') or k.startswith('L1_')}
+                       if k in ('prop_L', 'pcn_mean') or k[:3] in ('L0_', 'L1_', 'L2_')}
         if 'prop_L' not in self.arrays:
             raise ValueError("Proposal Covariance not set")
 
@@ -74,6 +78,8 @@ class LoweredProblem:
             if pre + "lv" in a:
                 p = a[pre + "lv"]
                 lv.alpha, lv.gamma, lv.T, lv.rk4_steps = float(p[0]), float(p[1]), float(p[2]), int(p[3])
+            if pre + "tempering" in a:
+                lv.tempered, lv.tempering = 1, float(np.asarray(a[pre + "tempering"]).reshape(-1)[0])
         return pb
 
 
@@ -89,7 +95,7 @@ class ChainEnsemble:
         self.n_chains = int(n_chains)
         self.dim = problem.dim
         self.levels = problem.levels
-        self.J = problem.J if problem.levels == 2 else 1
+        self.J = problem.J if problem.levels >= 2 else 1
         self.device = torch.device('cuda', int(device))
         cfg = YgConfig()
         cfg.abi_version = _lib.YG_ABI_VERSION
@@ -143,16 +149,30 @@ class ChainEnsemble:
             pass
 
     # ------------------------------------------------------------------ state
-    def set_state(self, theta0):
-        """theta0: [n_chains, d] (or [d], broadcast) host or device array."""
+    def set_state(self, theta0, keep_diagnostics=False, keep_adaptation=False, step_index=None):
+        """theta0: [n_chains, d] (or [d], broadcast) host or device array.
+
+        Resets the diagnostics (accept counters, Welford moments, evaluation counters) and the adaptation state
+        (adaptive-Metropolis moments / factors, adaptive error model) unless told to keep them -- the reference
+        keeps both across run() calls (diagnostics until clear()).  The Philox stream position is NOT reset: like
+        numpy's generator in the reference it keeps advancing, so a second run from the same state sees fresh
+        noise; pass step_index to reposition it (yg_seek)."""
         t = theta0.to(torch.float64) if torch.is_tensor(theta0) else torch.from_numpy(np.array(theta0, dtype=np.float64))
         if t.dim() == 1:
             t = t.reshape(1, -1).expand(self.n_chains, -1)
         if tuple(t.shape) != (self.n_chains, self.dim):
             raise ValueError(f"initial state must be [{self.n_chains}, {self.dim}], got {tuple(t.shape)}")
         soa = t.to(self.device).t().contiguous()            # [d, n]
+        flags = (_lib.KEEP_DIAGNOSTICS if keep_diagnostics else 0) | (_lib.KEEP_ADAPTATION if keep_adaptation else 0)
         with torch.cuda.device(self.device):
-            check(self.lib.yg_set_state(self._h, C.c_void_p(soa.data_ptr()), self._stream()))
+            check(self.lib.yg_set_state(self._h, C.c_void_p(soa.data_ptr()), flags, self._stream()))
+        if step_index is not None:
+            self.seek(step_index)
+        return self
+
+    def seek(self, step_index):
+        """Positions the Philox stream: the next run draws the noise of steps step_index, step_index + 1, ..."""
+        check(self.lib.yg_seek(self._h, int(step_index)))
         return self
 
     def set_proposal_factor(self, L):
@@ -247,7 +267,7 @@ class ChainEnsemble:
         with torch.cuda.device(self.device):
             check(self.lib.yg_get_state(self._h, C.byref(st), self._stream()))
         c = self.counters()
-        r['step_index'], r['welford_n'] = c['step_index'], c['welford_n']
+        r['step_index'], r['welford_n'], r['am_steps'] = c['step_index'], c['welford_n'], c['am_steps']
         return r
 
     def accept_counts(self):
@@ -278,15 +298,17 @@ class ChainEnsemble:
             st.aem_m2_dev, st.aem_cache_dev = keep['aem_m2'].data_ptr(), keep['aem_cache'].data_ptr()
         with torch.cuda.device(self.device):
             check(self.lib.yg_load_state(self._h, C.byref(st), int(r.get('step_index', 0)),
-                                         int(r.get('welford_n', 0)), self._stream()))
+                                         int(r.get('welford_n', 0)),
+                                         int(r.get('am_steps', r.get('welford_n', 0))), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()
         return self
 
     def counters(self):
-        buf = (C.c_int64 * 6)()
+        buf = (C.c_int64 * 8)()
         with torch.cuda.device(self.device):
             check(self.lib.yg_get_counters(self._h, buf, self._stream()))
-        keys = ('step_index', 'transitions', 'accepted', 'coarse_evals', 'fine_evals', 'welford_n')
+        keys = ('step_index', 'transitions', 'accepted', 'coarse_evals', 'fine_evals', 'welford_n', 'am_steps',
+                'mid_evals')
         c = dict(zip(keys, [int(x) for x in buf]))
         if self.levels == 1:        # single level: level 0 IS the target
             c['fine_evals'], c['coarse_evals'] = c['coarse_evals'], 0

@@ -60,7 +60,7 @@ def save_checkpoint(path, ensemble, extra=None):
     st = ensemble.state()
     arrays = {k: st[k].cpu().numpy() for k in _STATE_KEYS if k in st}
     head = dict(format='yagre_mcmc_b200.checkpoint', version=FORMAT_VERSION, step_index=int(st['step_index']),
-                welford_n=int(st['welford_n']), n_chains=int(ensemble.n_chains), dim=int(ensemble.dim),
+                welford_n=int(st['welford_n']), am_steps=int(st.get('am_steps', 0)), n_chains=int(ensemble.n_chains), dim=int(ensemble.dim),
                 levels=int(ensemble.levels), seed=int(ensemble.cfg.seed), chain_offset=int(ensemble.cfg.chain_offset),
                 model=ensemble.problem.model, adaptive=int(ensemble.cfg.adaptive), aem=int(ensemble.cfg.aem),
                 extra=extra or {})
@@ -84,5 +84,6 @@ def load_checkpoint(path, ensemble):
                              "a resumed run would not continue the saved chains")
     st = {k: torch.from_numpy(np.ascontiguousarray(f[k])) for k in _STATE_KEYS if k in f.files}
     st['step_index'], st['welford_n'] = head['step_index'], head['welford_n']
+    st['am_steps'] = head.get('am_steps', head['welford_n'])
     ensemble.load_state(st)
     return head
