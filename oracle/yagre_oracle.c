@@ -158,6 +158,7 @@ double yo_logpost(const yo_problem *pb, int lvl, const double *theta, int64_t *n
     const yo_level *L = &pb->level[lvl];
     const int d = pb->dim;
     double x[YO_MAX_DIM];
+    if (n_evals) (*n_evals)++;
     if (pb->model == YO_GAUSS) {
         for (int i = 0; i < d; i++) x[i] = theta[i] - L->g_mean[i];
         return -0.5 * quad_form(L->g_prec, x, d) + L->g_logconst;
@@ -165,7 +166,6 @@ double yo_logpost(const yo_problem *pb, int lvl, const double *theta, int64_t *n
     const int nD = L->n_data, dd = L->data_dim;
     double *q = (double *)malloc(sizeof(double) * (size_t)nD);
     double r[YO_MAX_DATA], F[YO_MAX_DATA];
-    if (n_evals) (*n_evals)++;
     if (pb->model == YO_LINEAR) {
         for (int k = 0; k < dd; k++) {               /* A @ theta + b  (exampleSetup.py:46) */
             double acc = 0.0;

@@ -170,13 +170,21 @@ def test_mlda_two_surrogates_through_the_builder():
     assert states.shape == (2000, 512, 2)
     assert 0.1 < mc.diagnostics.global_acceptance_rate() < 0.9
     np.testing.assert_allclose(states[500::5].reshape(-1, 2).mean(0), tgtMean, atol=0.1)
-    np.testing.assert_allclose(np.cov(states[500::5].reshape(-1, 2).T), tgtCov, atol=0.1)
+    # The reference's two-surrogate recursion is not an exact delayed-acceptance sampler (the screen uses the
+    # finest surrogate although the sub-chain ran on the base one, mlda.py:130,146-154): the UNMODIFIED reference,
+    # run here for 3 x 30,000 steps (seeds 1-3), gives covariance [[3.86, -0.86], [-0.86, 1.00]] and acceptance
+    # 0.52-0.53 on this problem, not the target's [[2.4, -0.5], [-0.5, 0.7]].  The drop-in reproduces that.
+    np.testing.assert_allclose(np.cov(states[500::5].reshape(-1, 2).T), [[3.86, -0.86], [-0.86, 1.0]], atol=0.12)
+    assert 0.50 < mc.diagnostics.global_acceptance_rate() < 0.55
     coarse, fine_ev = mc.evaluation_counts()
     assert coarse > 5.9 * 512 * 1999 and fine_ev <= 512 * 1999
-    b.surrogateTargets = [base, fine, fine]
-    b.subChainLengths = [3, 3, 3]
+    b3 = MLDABuilder()
+    b3.explicitTarget = tgt
+    b3.surrogateTargets = [base, fine, fine]
+    b3.baseProposalCovariance = IIDCovarianceMatrix(2, 1.0)
+    b3.subChainLengths = [3, 3, 3]
     with pytest.raises(NotImplementedError):
-        b.build_method()
+        b3.build_method()
 
 
 def test_consecutive_runs_use_fresh_noise_and_diagnostics_accumulate():

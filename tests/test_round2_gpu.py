@@ -242,7 +242,11 @@ def test_three_level_philox_run_replayed_through_oracle():
 
 
 def test_three_level_posterior_moments():
-    """reference test/test_mlda.py:62-91 (two surrogates, [6, 6]): acceptance in (0.1, 0.9), mean within 0.1."""
+    """reference test/test_mlda.py:62-91 (two surrogates, [6, 6]): acceptance in (0.1, 0.9), mean within 0.1.
+    The covariance is the one the UNMODIFIED reference produces on this problem (3 x 30,000 steps run in the
+    container: [[3.86, -0.86], [-0.86, 1.00]], acceptance 0.52-0.53) -- its two-surrogate recursion screens with
+    the finest surrogate although the sub-chain ran on the base one, so it does not reproduce the target's
+    [[2.4, -0.5], [-0.5, 0.7]]; a drop-in has to match the reference, not the textbook."""
     meta, arrays = _three_level_gauss()
     nc = 4096
     ens = _ens(meta, arrays, nc, seed=42)
@@ -252,9 +256,9 @@ def test_three_level_posterior_moments():
     s = ens.run(400, thin=5, samples=True)["samples"].cpu().numpy()
     c1 = ens.counters()
     flat = s.transpose(0, 2, 1).reshape(-1, 2)
-    np.testing.assert_allclose(flat.mean(0), [1.0, 1.5], atol=0.02)
-    np.testing.assert_allclose(np.cov(flat.T), [[2.4, -0.5], [-0.5, 0.7]], atol=0.05)
-    assert 0.1 < (c1["accepted"] - c0["accepted"]) / (c1["transitions"] - c0["transitions"]) < 0.9
+    np.testing.assert_allclose(flat.mean(0), [1.0, 1.5], atol=0.1)
+    np.testing.assert_allclose(np.cov(flat.T), [[3.86, -0.86], [-0.86, 1.0]], atol=0.1)
+    assert 0.50 < (c1["accepted"] - c0["accepted"]) / (c1["transitions"] - c0["transitions"]) < 0.55
 
 
 def test_tempered_surrogate_philox_replay():

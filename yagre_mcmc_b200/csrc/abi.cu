@@ -631,9 +631,9 @@ extern "C" int yg_run(yg_ensemble *e, int64_t n_steps, int32_t thin, const yg_ou
             yg_set_error("unknown noise mode %d", noise->mode);
             return YG_ERR_INVALID;
         }
-        if (!noise->z_dev || !noise->u_f_dev || (e->cfg.n_levels == 2 && !noise->u_c_dev)) {
+        if (!noise->z_dev || !noise->u_f_dev || (e->cfg.n_levels >= 2 && !noise->u_c_dev)) {
             yg_set_error("noise mode %d needs z_dev, u_f_dev%s", noise->mode,
-                         e->cfg.n_levels == 2 ? " and u_c_dev" : "");
+                         e->cfg.n_levels >= 2 ? " and u_c_dev" : "");
             return YG_ERR_INVALID;
         }
         a.noise_mode = noise->mode;

@@ -227,7 +227,7 @@ class ChainEnsemble:
             assert tuple(u_f.shape) == (n_steps, n)
             noise.z_dev, noise.u_f_dev = z.data_ptr(), u_f.data_ptr()
             keep += [z, u_f]
-            if self.levels == 2:
+            if self.levels >= 2:
                 u_c = torch.as_tensor(inject['u_c'], dtype=torch.float64).to(self.device).contiguous()
                 assert tuple(u_c.shape) == (n_steps, J, n)
                 noise.u_c_dev = u_c.data_ptr()
