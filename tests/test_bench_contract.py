@@ -24,13 +24,17 @@ def _run(args, timeout):
 
 @pytest.mark.timeout(300)
 def test_reference_arm_line():
-    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1.0"], 280)
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1.0", "--ess-steps", "600"], 280)
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "chain-steps/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # ESS/s is half of BASELINE.json's metric: the CPU arm reports it too, with the cores it used
+    assert d["cpu_baseline"]["ess_per_s"] > 0 and d["ess"]["cores"] == d["cpu_baseline"]["cores"] == d["cores"]
+    py = d["cpu_baseline"]["python_reference"]
+    assert py["rk4_plugin"]["chain_steps_per_s_per_core"] > 0 and "NOT on this box" in py["measured_in"]
 
 
 @pytest.mark.gpu
@@ -43,9 +47,15 @@ def test_b200_arm_line():
     rf = d["roofline"]
     assert rf["bound"] == "fp64" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert 0.0 < rf["rk4_loop"]["frac"] < 1.0 and rf["executed"]["fp64_instr_per_rk4_step"] == 20
+    assert abs(rf["frac_executed"] - rf["frac"] * 40.0 / 58.0) < 1e-9 and rf["frac_of_bare_rk4_loop"] == rf["rk4_loop"]["frac"]
+    assert rf["traffic"] is None and "no committed ncu capture" in rf["traffic_source"]       # no capture at 8,192 chains
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 8192 * 2 * 8 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= 1.05 * d["value"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["ess_per_s"] > 0
+    assert d["cpu_cores"] == d["cpu_baseline"]["cores"] and d["scaling"] == "weak"
+    for arm in ("pooled", "adaptive"):
+        assert d["ess"][arm]["ess_per_s"] > 0 and d["ess"][arm]["degenerate_chains"] == 0
+        assert all(abs(x - 1.0) < 0.05 for x in d["ess"][arm]["diagnostics"]["split_rhat"])
     dg = d["ess"]["diagnostics"]
     assert dg["n_chains"] == 8192 and all(abs(x - 1.0) < 0.05 for x in dg["rhat"] + dg["split_rhat"])
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
