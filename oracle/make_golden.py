@@ -284,12 +284,12 @@ def big_linear_problem(d=16, dataDim=24, nData=3, seed=3):
                 priorVar=2.0, propVar=0.004, truth=truth, d=d, dataDim=dataDim)
 
 
-def case_big_linear(twoLevel):
+def case_big_linear(twoLevel, name=None, **pkw):
     from yagremcmc.chain.target import UnnormalisedPosterior
-    p = big_linear_problem()
+    p = big_linear_problem(**pkw)
     d, dd = p['d'], p['dataDim']
     nChains, nSteps, J = 3, 150, (2 if twoLevel else 1)
-    rng = Generator(Philox(1300 + J))
+    rng = Generator(Philox(1300 + J + 7 * len(pkw)))
     z, u_c, u_f = make_noise(rng, nChains, nSteps, J, d, zero_at=[(0, 4, None)] if twoLevel else [(0, 4, 0)])
     theta0 = p['truth'] + 0.05 * rng.standard_normal((nChains, d))
     traj, acc, lpc, lpf = [], [], [], []
@@ -329,8 +329,41 @@ def case_big_linear(twoLevel):
         arrays.update(level('f', 'L0_'))
         arrays.update(logpost_L0=lpf)
     meta = dict(model='linear', dim=d, levels=2 if twoLevel else 1, J=J, eq='exact',
-                note='GEMM-sized linear model d=16, dataDim=24, nData=3 (reference chain stack + exampleSetup-style A@theta+b)')
-    save("mlda_linear_big" if twoLevel else "mrw_linear_big", meta, arrays)
+                note=f'GEMM-sized linear model d={d}, dataDim={dd}, nData={p["data"].shape[0]} (reference chain stack + exampleSetup-style A@theta+b)')
+    save(name or ("mlda_linear_big" if twoLevel else "mrw_linear_big"), meta, arrays)
+
+
+def case_pcn_big_linear():
+    """pCN (chain/method/pcn.py) on the GEMM-sized linear model: diagonal centred Gaussian prior, likelihood-only target."""
+    p = big_linear_problem(d=12, dataDim=20, nData=2, seed=5)
+    d, dd = p['d'], p['dataDim']
+    nChains, nSteps, step = 3, 150, 0.002
+    rng = Generator(Philox(1390))
+    z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, d, zero_at=[(0, 6, 0)])
+    priorVar = np.linspace(0.5, 2.0, d)
+    theta0 = p['truth'] + 0.05 * rng.standard_normal((nChains, d))
+    traj, acc, lp = [], [], []
+    for c in range(nChains):
+        data = rh.Data(p['data'])
+        noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(dd, p['noiseVar']))
+        lik = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_f'], p['b_f'])), noise)
+        prior = rh.Gaussian(rh.ParameterVector(np.zeros(d)), rh.DiagonalCovarianceMatrix(priorVar))
+        inj = rh.NoiseInjector(z[c], None, u_f[c])
+        b = rh.PCNBuilder()
+        b.bayesModel = rh.BayesianRegressionModel(lik, prior)
+        b.stepSize = step
+        mcmc = rh.quiet(b.build_method)
+        t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(theta0[c].copy()), nSteps, inj, False)
+        traj.append(t); acc.append(a)
+        lp.append(logpost_along(lik, rh.ParameterVector, t))
+        print(f"    pcn_linear_big chain {c}: acceptance {a.mean():.3f}")
+    arrays = dict(prop_L=lower_proposal('diag', priorVar, d), pcn_mean=np.zeros(d), theta0=theta0, z=z, u_c=u_c, u_f=u_f,
+                  traj=traj, accepted=acc, logpost_L0=lp,
+                  L0_data=p['data'], L0_noise_prec=diag_precision(p['noiseVar'], dd), L0_prior_mean=np.zeros(d),
+                  L0_prior_prec=np.zeros((d, d)), L0_G=p['G_f'], L0_b=p['b_f'])
+    meta = dict(model='linear', dim=d, levels=1, J=1, eq='exact', proposal='pcn', pcn_step=step,
+                note='pCN on a GEMM-sized linear model (d=12, dataDim=20, nData=2), diagonal centred Gaussian prior')
+    save("pcn_linear_big", meta, arrays)
 
 
 # --------------------------------------------------------------------------
@@ -918,6 +951,9 @@ if __name__ == "__main__":
     if want('biglinear'):
         case_big_linear(False)
         case_big_linear(True)
+    if want('biglinear2'):
+        case_big_linear(False, name="mrw_linear_big_rows12", d=10, dataDim=33, nData=12, seed=4)     # more than 8 data rows
+        case_pcn_big_linear()
     if want('post'):
         case_postprocessing()
     if want('lv'):

@@ -338,3 +338,79 @@ def test_iat_constant_series_reports_zero_ess():
             assert iat[3] == ns and ess[3] == 0
         for c in (0, 2, 5):
             assert 1 <= iat[c] < 10 and ess[c] == ns // iat[c]
+
+
+# ------------------------------------------------------------------------------------------
+# the FP64 tensor path (linear_dmma_kernel.cu): normals, balanced schedule, Philox == recorded
+# ------------------------------------------------------------------------------------------
+def test_dmma_path_normals_match_the_oracle_transform():
+    """the Box-Muller transform of the tensor-path kernel runs in FP32 but from the oracle's
+    uniforms (u1 = (k1 + 1) 2^-53 through log / log1p, sign bit + 52-bit angle): the device normals equal
+    cport.philox_normals (FP64 transform) to |dz| <= 4e-6 (1 + |z|), are exactly sign symmetric in construction and
+    never give a zero radius short of u1 = 1."""
+    from oracle import cport
+    meta, arrays = bp.big_linear_problem(23, 45, 3)
+    nc, ns, seed = 96, 40, 4242
+    ens = _ens(meta, arrays, nc, seed=seed, chain_offset=1000)
+    ens.set_state(np.zeros((nc, 23)))
+    out = ens.run(ns, samples=False, record=True)
+    z = out["z"].cpu().numpy()                               # [ns, 1, d, nc]
+    worst = 0.0
+    for c in (0, 1, 17, 95):
+        for n in range(ns):
+            want = cport.philox_normals(seed, 1000 + c, n, 0, 23)
+            err = np.abs(z[n, 0, :, c] - want) / (1.0 + np.abs(want))
+            worst = max(worst, err.max())
+    assert worst <= 4e-6, worst
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1.0) < 0.02 and np.all(z != 0.0)
+    assert abs((z > 0).mean() - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("case", ["single_64x256", "two_level_32x96", "ragged_23x45"])
+def test_dmma_philox_launch_equals_recorded_launch_and_is_shard_invariant(case):
+    """The production instance (Philox only) and the recording instance of linear_dmma_mh_kernel draw the same noise
+    and run the same arithmetic: bit-identical samples.  And the balanced (tile, step-range) schedule hands chains
+    from warp to warp inside a launch without changing a bit: chains [off, off + m) of a large ensemble equal the
+    same chains run alone in a small handle."""
+    if case == "single_64x256":
+        (meta, arrays), d, nc, ns = bp.big_linear_problem(64, 256, 1), 64, 20000, 13
+    elif case == "two_level_32x96":
+        (meta, arrays), d, nc, ns = bp.big_linear_problem(32, 96, 2, two_level=True, J=3), 32, 20000, 9
+    else:
+        (meta, arrays), d, nc, ns = bp.big_linear_problem(23, 45, 3), 23, 4999, 11
+    th0 = 0.01 * np.random.default_rng(3).standard_normal((nc, d))
+    runs = []
+    for record in (False, True):
+        ens = _ens(meta, arrays, nc, seed=12)
+        ens.set_state(th0)
+        o1 = ens.run(ns, samples=True, accepted=True, logpost=True, record=record)
+        o2 = ens.run(5, samples=True, thin=5, record=record)                 # continues: stream position, Welford
+        runs.append((o1, o2, ens.state(), ens.counters()))
+    for k in ("samples", "accepted", "logpost"):
+        assert torch.equal(runs[0][0][k], runs[1][0][k]), k
+    assert torch.equal(runs[0][1]["samples"], runs[1][1]["samples"])
+    assert runs[0][3] == runs[1][3]
+    for k in ("theta", "logpost", "n_accept", "w_mean", "w_m2"):
+        assert torch.equal(runs[0][2][k], runs[1][2][k]), k
+    off, m = 8000 if nc > 10000 else 1234, 800
+    sub = _ens(meta, arrays, m, seed=12, chain_offset=off)
+    sub.set_state(th0[off:off + m])
+    s1 = sub.run(ns, samples=True, accepted=True, logpost=True)
+    for k in ("samples", "accepted", "logpost"):
+        assert torch.equal(s1[k], runs[0][0][k][..., off:off + m]), k
+    s2 = sub.run(5, samples=True, thin=5)
+    assert torch.equal(s2["samples"], runs[0][1]["samples"][..., off:off + m])
+    st = sub.state()        # Welford is kept in run-length form: the grouping of its updates follows the launch boundaries
+    np.testing.assert_allclose(st["w_mean"].cpu().numpy(), runs[0][2]["w_mean"][:, off:off + m].cpu().numpy(), rtol=1e-11, atol=1e-14)
+    assert torch.equal(st["n_accept"], runs[0][2]["n_accept"][off:off + m])
+    # replay of the recorded launch through the oracle on a sample of chains
+    from oracle import cport
+    rows = np.arange(0, nc, max(1, nc // 40))[:40]
+    idx = torch.from_numpy(rows).to("cuda")
+    o1 = runs[1][0]
+    rec = {k: o1[k].index_select(o1[k].dim() - 1, idx) for k in ("z", "u_c", "u_f", "samples", "accepted", "logpost")}
+    ref = _replay(meta, arrays, th0[rows], rec)
+    assert int((rec["accepted"].cpu().numpy().T != ref["accepted"]).sum()) == 0
+    assert rel_err(rec["samples"].cpu().numpy().transpose(2, 0, 1), ref["traj"][:, 1:]).max() <= 1e-12
+    lp = rec["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, -1], ref["logpost_L1" if meta["levels"] == 2 else "logpost_L0"][:, 1:]).max() <= LOGPOST_RTOL

@@ -111,10 +111,24 @@ bool is_diagonal(const double *M, int n)
 int set_problem_big(yg_ensemble *e, const yg_problem *pb)
 {
     const int d = e->cfg.dim, nl = e->cfg.n_levels;
-    if (pb->proposal != YG_PROPOSAL_MRW || e->cfg.adaptive || e->cfg.eq_mode != YG_EQ_EXACT || e->cfg.aem || nl > 2) {
-        yg_set_error("large linear model (dim > %d or data_dim > %d): MRW / two-level delayed acceptance with exact "
+    if (e->cfg.adaptive || e->cfg.eq_mode != YG_EQ_EXACT || e->cfg.aem || nl > 2) {
+        yg_set_error("large linear model (dim > %d or data_dim > %d): MRW / pCN / two-level delayed acceptance with exact "
                      "equality only (no adaptive proposal, adaptive error model or third level)", YG_MAX_DIM, YG_MAX_DATA_DIM);
         return YG_ERR_UNSUPPORTED;
+    }
+    if (pb->proposal != YG_PROPOSAL_MRW && pb->proposal != YG_PROPOSAL_PCN) {
+        yg_set_error("unknown proposal kind %d", pb->proposal);
+        return YG_ERR_INVALID;
+    }
+    if (pb->proposal == YG_PROPOSAL_PCN) {
+        if (!(pb->pcn_step > 0.0 && pb->pcn_step <= 0.5)) {       // pcn.py:42
+            yg_set_error("pCN step size must lie in (0, 0.5], got %g", pb->pcn_step);
+            return YG_ERR_INVALID;
+        }
+        if (nl != 1) {
+            yg_set_error("pCN is a single-level method (chain/method/pcn.py)");
+            return YG_ERR_UNSUPPORTED;
+        }
     }
     for (int l = 0; l < nl; l++)
         if (pb->level[l].tempered) {
@@ -134,19 +148,23 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
             yg_set_error("level %d: linear level needs data, noise_prec, prior, G and b", l);
             return YG_ERR_INVALID;
         }
-        if (L.data_dim > YG_BIG_MAX_DATA_DIM || L.n_data > YG_BIG_MAX_ROWS) {
-            yg_set_error("level %d: large linear model is limited to data_dim <= %d and n_data <= %d", l,
-                         YG_BIG_MAX_DATA_DIM, YG_BIG_MAX_ROWS);
+        if (L.data_dim > YG_BIG_MAX_DATA_DIM) {
+            yg_set_error("level %d: large linear model is limited to data_dim <= %d", l, YG_BIG_MAX_DATA_DIM);
             return YG_ERR_UNSUPPORTED;
         }
         if (!is_diagonal(L.noise_prec, L.data_dim) || !is_diagonal(L.prior_prec, d)) {
             yg_set_error("level %d: large linear model needs diagonal noise and prior precision", l);
             return YG_ERR_UNSUPPORTED;
         }
-        const size_t np = (size_t)(L.data_dim + 7) & ~size_t(7);
-        tail_len += np * ks + np * 2 + 2 * (size_t)kp;
+        for (int r = 0; r < L.data_dim; r++)
+            if (!(L.noise_prec[(size_t)r * L.data_dim + r] >= 0.0)) {
+                yg_set_error("level %d: negative noise precision", l);
+                return YG_ERR_INVALID;
+            }
+        const size_t np = (size_t)(L.data_dim + 15) & ~size_t(15);
+        tail_len += np * ks + np + 2 * (size_t)kp;
     }
-    tail_len += kp;
+    tail_len += 2 * (size_t)kp;
     tail_len = (tail_len + 1) & ~size_t(1);
     if (sizeof(double) * (tail_len + (size_t)16 * 8 * ks) > 226 * 1024) {      // blob + per-warp state tiles (16 warps x 8 chains)
         yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
@@ -158,19 +176,22 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     h->dim = d; h->kp = kp; h->ks = ks; h->n_levels = nl;
     h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
     h->tail_len = (int32_t)tail_len;
+    h->proposal = pb->proposal;
+    if (pb->proposal == YG_PROPOSAL_PCN) {
+        const double t = 2.0 * pb->pcn_step;                      // pcn.py:30
+        h->pcn_a = sqrt(1.0 - t);
+        h->pcn_b = sqrt(t);
+    }
     size_t off = 0;
     for (int l = 0; l < nl; l++) {
         const yg_level &L = pb->level[l];
         BigLevel &B = h->lvl[l];
-        const int np = (L.data_dim + 7) & ~7;
+        const int np = (L.data_dim + 15) & ~15;
         B.n_data = L.n_data; B.data_dim = L.data_dim; B.np = np;
         B.G_off = (int32_t)off;
-        for (int r = 0; r < L.data_dim; r++)
-            for (int k = 0; k < d; k++) tail[off + (size_t)r * ks + k] = L.G[(size_t)r * d + k];
-        off += (size_t)np * ks;
-        // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + sum_col P_col sum_rows (d - mean)^2
-        B.bd_off = (int32_t)off;
-        B.nw_off = (int32_t)(off + np);
+        B.bd_off = (int32_t)(off + (size_t)np * ks);
+        // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + sum_col P_col sum_rows (d - mean)^2;
+        // sqrt(n P_col) is folded into row `col` of G and into b - mean
         double q_const = 0.0;
         for (int r = 0; r < L.data_dim; r++) {
             double mean = 0.0;
@@ -182,12 +203,13 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
                 scatter += dd * dd;
             }
             const double prec = L.noise_prec[(size_t)r * L.data_dim + r];
-            tail[off + r] = L.b[r] - mean;
-            tail[off + np + r] = (double)L.n_data * prec;
+            const double sw = sqrt((double)L.n_data * prec);
+            for (int k = 0; k < d; k++) tail[off + (size_t)r * ks + k] = sw * L.G[(size_t)r * d + k];
+            tail[B.bd_off + r] = sw * (L.b[r] - mean);
             q_const += prec * scatter;
         }
         B.q_const = q_const;
-        off += 2 * (size_t)np;
+        off += (size_t)np * ks + np;
         B.pmean_off = (int32_t)off;
         for (int k = 0; k < d; k++) tail[off + k] = L.prior_mean[k];
         off += kp;
@@ -198,11 +220,20 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     if (nl == 1) h->lvl[1] = h->lvl[0];
     h->propL_off = (int32_t)off;
     for (int k = 0; k < d; k++) tail[off + k] = pb->prop_L[(size_t)k * d + k];
+    off += kp;
+    h->pcn_mean_off = (int32_t)off;
+    if (pb->proposal == YG_PROPOSAL_PCN && pb->pcn_mean)
+        for (int k = 0; k < d; k++) tail[off + k] = pb->pcn_mean[k];
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    e->problem_set = false;
     if (e->d_problem) cudaFree(e->d_problem);
     e->d_problem = nullptr;
     YG_CUDA_CHECK(cudaMalloc((void **)&e->d_problem, blob.size()));
     YG_CUDA_CHECK(cudaMemcpy(e->d_problem, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    if (!e->big_done) {     // per-tile progress counters of the balanced (tile, step-range) schedule
+        int rc = dev_alloc(&e->big_done, ((size_t)e->cfg.n_chains + 7) / 8);
+        if (rc) return rc;
+    }
     e->h_problem.swap(blob);
     e->problem_set = true;
     e->big = true;
@@ -335,6 +366,7 @@ extern "C" int yg_destroy(yg_ensemble *e)
     cudaFree(e->n_accept);
     cudaFree(e->counters);
     cudaFree(e->pool_partials);
+    cudaFree(e->big_done);
     delete e;
     return YG_OK;
 }
@@ -581,6 +613,10 @@ extern "C" int yg_set_proposal_factor(yg_ensemble *e, const double *L_host, void
             return YG_ERR_UNSUPPORTED;
         }
         DevBigHeader *h = reinterpret_cast<DevBigHeader *>(e->h_problem.data());
+        if (h->proposal != YG_PROPOSAL_MRW) {
+            yg_set_error("the proposal factor of a pCN chain is the prior's (pcn.py:23-35) and cannot be replaced");
+            return YG_ERR_UNSUPPORTED;
+        }
         double *tail = reinterpret_cast<double *>(e->h_problem.data() + sizeof(DevBigHeader));
         for (int k = 0; k < d; k++) tail[h->propL_off + k] = L_host[(size_t)k * d + k];
         char *dst = reinterpret_cast<char *>(e->d_problem) + sizeof(DevBigHeader) + sizeof(double) * h->propL_off;

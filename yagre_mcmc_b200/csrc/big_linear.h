@@ -4,22 +4,24 @@
 #include <stdint.h>
 #include "../../include/yagre_b200.h"
 
-#define YG_BIG_MAX_ROWS 8         /* data rows (n_data) */
-
 struct BigLevel {
-    int32_t n_data, data_dim, np, _pad;             // np = data_dim rounded up to a multiple of 8
-    int32_t G_off, bd_off, nw_off, pmean_off;       // offsets (doubles) into the tail
-    int32_t pprec_off, _pad2[3];
+    int32_t n_data, data_dim, np, _pad;             // np = data_dim rounded up to a multiple of 16 (one m16n8k4 row block)
+    int32_t G_off, bd_off, pmean_off, pprec_off;    // offsets (doubles) into the tail
     double q_const, _pad3;                          // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
 };
 
 struct DevBigHeader {
     int32_t dim, kp, ks, n_levels;                  // kp in {16, 32, 64} >= dim; ks = kp + 4 (row stride of G)
-    int32_t J, tail_len, propL_off, _pad;
+    int32_t J, tail_len, propL_off, proposal;       // proposal: yg_proposal
+    int32_t pcn_mean_off, _pad[3];
+    double pcn_a, pcn_b;                            // sqrt(1 - 2h), sqrt(2h)   (pcn.py:30-35)
     BigLevel lvl[2];
-    // followed by double tail[tail_len]: per level G[np][ks], bd[np] = b - mean_rows(data),
-    // nw[np] = n_data * noise precision, pmean[kp], pprec[kp]; then propL[kp].  Padding is zero.
-    // sum_rows ||F - d_row||^2_P = sum_col nw_col (F_col - mean_col)^2 + q_const.
+    // followed by double tail[tail_len]: per level
+    //   Gw[np][ks] = sqrt(w_row) G_row,  bdw[np] = sqrt(w_row) (b_row - mean over the data rows),  w = n_data * noise
+    //   precision (the weights are folded into the operands once on the host, so the accumulator epilogue is one add
+    //   and one FMA per element), pmean[kp], pprec[kp];
+    // then propL[kp] and pcn_mean[kp].  Padding is zero.
+    // sum_rows ||F - d_row||^2_P = sum_col w_col (F_col - mean_col)^2 + q_const.
 };
 static_assert(sizeof(DevBigHeader) % 16 == 0, "header must keep 16-byte alignment");
 

@@ -60,6 +60,7 @@ struct yg_ensemble {
     int aem_data_dim = 0;
     unsigned long long *n_accept = nullptr, *counters = nullptr;
     double *pool_partials = nullptr;   // [POOL_PARTS][yg_pooled_len(d)] scratch of yg_pooled_stats
+    long long *big_done = nullptr;     // [tiles] steps completed per 8-chain tile within a launch (linear_dmma_kernel.cu)
     int64_t step_index = 0, welford_n = 0, am_steps = 0;
     int last_grid = 0, last_block = 0, last_smem = 0;
     int64_t launches = 0;

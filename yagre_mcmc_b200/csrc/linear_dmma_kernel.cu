@@ -1,48 +1,53 @@
 // linear_dmma_kernel.cu -- Metropolis-Hastings over an ensemble of chains on the LINEAR model
 // F = G theta + b when the parameter / data dimensions are too large for one chain per thread
 // (d up to 64, data_dim up to 256): the forward model of a tile of chains is a dense FP64 GEMM
-// [chains x d] . [d x data_dim], issued on the FP64 tensor path (DMMA, mma.sync m16n8k4.f64),
+// [data_dim x d] . [d x chains], issued on the FP64 tensor path (DMMA, mma.sync m16n8k4.f64),
 // with the Gaussian-misfit log-likelihood fused into the accumulator epilogue.
 //
 // Reference semantics restated (rkutri/yagre-mcmc):
 //   linear forward       exampleSetup.py:42-52 (A @ theta + b, broadcast against the data rows)
 //   likelihood / prior   statistics/likelihood.py:33-39,74-84, statistics/gaussian.py:19-24,
 //                        statistics/covariance.py:19-22,54-55 (diagonal precisions)
-//   proposal             statistics/gaussian.py:61-66 with a diagonal factor (covariance.py:51-52)
+//   proposal             statistics/gaussian.py:61-66 with a diagonal factor (covariance.py:51-52);
+//                        pCN: chain/method/pcn.py:23-35
 //   MRW / MLDA ratios    chain/method/mrw.py:51-57, chain/method/mlda.py:100-110,146-154
 //   step loop            chain/metropolisHastings.py:55-120
 //   Welford diagnostics  chain/diagnostics.py:91-94, statistics/estimation.py:36-53 (diagonal M2)
 //
-// B200 mapping
-//   * persistent CTAs (one per SM), 16 warps; a warp owns a tile of 8 chains (the M extent of
-//     m8n8k4 = the native DMMA.8x8x4) for ALL n_steps: 8-row tiles halve the registers per thread
-//     (d = 64: 32 per operand copy), so 16 warps are resident and the non-GEMM work of a warp
-//     (noise, accept, Welford) overlaps the GEMMs of three others on its sub-partition.  Proposals live in registers in A-fragment layout: lane
-//     (g = lane / 4, t = lane % 4) holds p[row g][k = 4 i + t], so a proposal is already
-//     the A operand of the GEMM; the current state of the tile sits in a per-warp shared-memory
-//     tile in the same lane-private pattern (d = 64 needs 64 registers per operand copy);
-//   * G of every level is staged once per CTA into shared memory (row stride = 4 mod 16 doubles:
-//     the B-fragment loads of a warp are bank-conflict free) and shared by the 16 warps: one 8-byte
-//     load per lane and DMMA, half of the shared-memory bandwidth at full DMMA rate;
-//   * epilogue per 8x8 accumulator tile: + b, - data row, * noise precision, squared, summed
-//     per chain; a 4-lane butterfly finishes the row sums, so the four lanes of a chain hold
-//     bit-identical log-posteriors and take the same accept decision without further traffic;
-//   * Philox noise is keyed like the one-chain-per-thread kernels (seed, global chain id, step,
-//     sub-step, pair); the Box-Muller transform of this kernel runs in FP32 (see
-//     philox_normal_pair_f32): d normals per chain-step make the transform, not the GEMM, the
-//     limiter otherwise.
+// B200 mapping (measured facts: tools/probe_dmma.cu, profiles/r02_linear_dmma.md)
+//   * On B200 DMMA executes on the FP64 units themselves: DMMA.8x8x4 occupies a sub-partition's FP64 pipe for 16
+//     cycles, FP64 vector instructions queue behind it (a DFMA + DMMA mix takes the SUM of the two times), and a
+//     DMMA that depends on the previous one issues only every 26 cycles.  The roofline of this kernel is therefore
+//     the FP64 pipe shared by the GEMM and every DADD / DMUL / DFMA around it, and one warp alone must be able to
+//     keep the pipe full.
+//   * "swap-AB" GEMM on m16n8k4: G is the A operand (16 data rows x 4 parameters per instruction, two 8-byte
+//     shared-memory loads), the 8 chains of the warp are the N extent.  ptxas schedules the accumulator chains of a
+//     pass one after the other whatever the source order; an m16n8k4 is two DMMA.8x8x4 on separate accumulator
+//     halves, so even a single dependent chain issues at the full rate (32.5 cycles per m16n8k4, measured), where
+//     the m8n8k4 formulation of round 1 ran at 16 / 26 of it unless two warps happened to overlap.
+//   * a warp owns a tile of 8 chains; proposals live in registers in the B-fragment layout -- lane (g = lane / 4,
+//     t = lane % 4) holds p[chain g][k = 4 i + t] -- so a proposal IS the GEMM operand; the current state of the
+//     tile sits in a per-warp shared-memory tile in the same lane-private pattern;
+//   * G of every level is staged once per CTA into shared memory (row stride = 4 mod 16 doubles: the A-fragment
+//     loads of a warp are bank-conflict free), pre-multiplied by sqrt(n_data x noise precision) on the host, as is
+//     b - mean(data): the epilogue per accumulator element is one DADD and one DFMA (every FP64 vector instruction
+//     costs GEMM time);
+//   * the accumulators hold F[row][chain]: a lane sums the squares of its rows for chains 2t and 2t + 1, a
+//     butterfly over the row lanes finishes the sums and one shuffle hands every lane the value of ITS chain, so
+//     the four lanes of a chain hold bit-identical log-posteriors and take the same accept decision;
+//   * balanced schedule: the (tile, step) pairs of a launch are cut into equal contiguous ranges, one per warp of
+//     the persistent grid.  A warp first runs the HEAD of the tile its range ends in, then its whole tiles, then
+//     the TAIL of the tile its range starts in -- whose head the previous warp ran first -- with the chain state
+//     handed over through global memory and a per-tile progress counter.  No warp idles while another still has
+//     tiles (with whole tiles per warp 65,536 chains on 148 x 16 warps wasted 13.5 % of the launch);
+//   * Philox noise is keyed like the one-chain-per-thread kernels (seed, global chain id, step, sub-step, pair); the
+//     Box-Muller transform of this kernel runs in FP32 (see philox_normal_pair_f32): d normals per chain-step on
+//     the FP64 pipe would cost as much as a fifth of the GEMM.
 #include "ensemble.h"
 #include "big_linear.h"
 #include <math_constants.h>
 
 namespace {
-
-YG_DEVFN void dmma_m8n8k4(double &c0, double &c1, double a0, double b0)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a0), "d"(b0));
-}
 
 YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double b0)
 {
@@ -52,24 +57,33 @@ YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, doubl
         : "d"(a0), "d"(a1), "d"(b0));
 }
 
-// Box-Muller on one Philox block with the TRANSFORM in FP32: the two uniforms keep their 53 Philox bits, but
-// log / sqrt / sincospi run on the FP32 pipe (a few dozen FMA-pipe instructions instead of ~150 FP64 ones per
-// pair).  The normals are exact N(0,1) draws up to a relative perturbation of ~1e-7 -- immaterial for a proposal
-// distribution -- and a recorded stream replays bit-exactly.  This kernel draws d normals per chain and step
-// (64 at d = 64) against 2 in the LV kernel, where the FP64 transform stays.
-// Not inlined on purpose: inlined copies (Philox rounds + logf + sincospif) per proposal made the step loop
-// larger than the instruction cache (stall reason no_instruction 2.9 warps per issue in the ncu capture).
+// Box-Muller on one Philox block with the TRANSFORM in FP32 (the FP32 / SFU pipes are idle next to the GEMM, the
+// FP64 pipe is not).  Same uniforms as the oracle's yo_philox_normals: u1 = (k1 + 1) 2^-53 in (0, 1] and
+// u2 = k2 2^-53 in [0, 1) from the 53 high bits of the two word pairs; z = sqrt(-2 ln u1) (cos, sin)(2 pi u2).
+//   * -ln u1 keeps its relative accuracy over the whole range: for u1 > 1/2 it is -log1pf(-(1 - u1)) with
+//     1 - u1 = (2^53 - k1 - 1) 2^-53 formed exactly in integers (a float of u1 itself would round to 1 for
+//     u1 > 1 - 2^-25 and give a zero radius, i.e. a spurious "proposal == state"); the radius is zero only for
+//     u1 = 1, with probability 2^-53, exactly like the FP64 transform;
+//   * the top bit of k2 is the SIGN of (cos, sin) -- (cos, sin)(x + pi) = -(cos, sin)(x) -- and the other 52 bits
+//     the angle in [0, pi): P(z) = P(-z) holds exactly, not up to the float grid of the angle.
+// The normals equal the oracle's FP64 ones to |dz| <= 4e-6 (1 + |z|) (tests/test_round2_gpu.py); a recorded stream
+// replays bit-exactly.  Not inlined on purpose: inlined copies (Philox rounds + logf + sincospif) per proposal made
+// the step loop larger than the instruction cache (profiles/r01_linear_dmma.md).
 __device__ __noinline__ void philox_normal_pair_f32(uint64_t seed, uint64_t chain, uint64_t step, uint32_t sub, uint32_t b,
                                                     double &z0, double &z1)
 {
     const uint4 w = philox_block(seed, chain, step, sub, b);
-    const float u1 = (float)(u53(w.x, w.y) + 0x1.0p-53);   // (0,1]
-    const float u2 = (float)u53(w.z, w.w);
-    const float R = sqrtf(-2.0f * logf(u1));
+    const uint64_t m1 = ((((uint64_t)w.x << 32) | w.y) >> 11) + 1ull;          // [1, 2^53]: u1 = m1 2^-53
+    const uint64_t k2 = (((uint64_t)w.z << 32) | w.w) >> 11;                   // [0, 2^53): u2 = k2 2^-53
+    float nl;                                                                   // -ln u1 >= 0
+    if (m1 > (1ull << 52)) nl = -log1pf(-((float)((1ull << 53) - m1) * 0x1.0p-53f));
+    else nl = -logf((float)m1 * 0x1.0p-53f);
+    const float R = sqrtf(2.0f * nl);
     float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    z0 = (double)(R * cs);
-    z1 = (double)(R * sn);
+    sincospif((float)(k2 & ((1ull << 52) - 1ull)) * 0x1.0p-52f, &sn, &cs);      // 2 pi u2 = pi (top bit) + pi (low bits) 2^-52
+    const float sg = (k2 >> 52) ? -R : R;
+    z0 = (double)(sg * cs);
+    z1 = (double)(sg * sn);
 }
 
 YG_DEVFN double quad_sum(double v)
@@ -80,57 +94,67 @@ YG_DEVFN double quad_sum(double v)
 }
 
 struct SmemLevel {
-    const double *G;        // [np][ks]
-    const double *bd;       // [np]   b - mean over the data rows (likelihood.py:74-75 broadcasts F against the rows)
-    const double *nw;       // [np]   n_data * noise precision (zero beyond data_dim)
+    const double *G;        // [np][ks]  sqrt(w_row) G_row, w = n_data * noise precision
+    const double *bd;       // [np]      sqrt(w_row) (b - mean over the data rows)   (likelihood.py:74-75 broadcasts F against the rows)
     const double *pmean;    // [kp]
     const double *pprec;    // [kp]   (zero beyond dim)
     double q_const;         // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
-    int np;
+    int np;                 // data_dim rounded up to a multiple of 16
 };
 
-// log-posterior of the chain (row g of the warp's 8 x d tile) whose parameters are spread over the quad:
+// log-posterior of the chain (column g of the warp's d x 8 tile) whose parameters are spread over the quad:
 // a[i] = theta[4 i + t].  Every lane of a quad returns the same value.
 template <int KQ>
 YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)[KQ], const int g, const int t)
 {
-    // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + q_const  (exact identity;
-    // no cancellation: the row scatter is a precomputed constant)
-    double q = 0.0;
-    auto epilogue = [&](const int nb, const double c0, const double c1) {
-        const int col = nb + 2 * t;                                      // even: one 16-byte load per operand pair
-        const double2 bd = *reinterpret_cast<const double2 *>(L.bd + col);
-        const double2 nw = *reinterpret_cast<const double2 *>(L.nw + col);
-        const double e0 = c0 + bd.x, e1 = c1 + bd.y;                    // A @ theta + b - mean(data)
-        q = fma(nw.y * e1, e1, fma(nw.x * e0, e0, q));
+    // sum_rows ||F - d_row||^2_P = sum_col w_col (F_col - mean_col)^2 + q_const  (exact identity; no cancellation:
+    // the row scatter is a precomputed constant).  Accumulator layout of m16n8k4 with G as the A operand:
+    // c0, c1 = F[row nb + g][chains 2t, 2t + 1], c2, c3 = F[row nb + 8 + g][the same chains].
+    double qa = 0.0, qb = 0.0;                 // partial sums of chains 2t and 2t + 1 over this lane's rows
+    auto epilogue = [&](const int nb, const double c0, const double c1, const double c2, const double c3) {
+        const double b0 = L.bd[nb + g], b1 = L.bd[nb + 8 + g];
+        const double e0 = c0 + b0, e1 = c1 + b0, e2 = c2 + b1, e3 = c3 + b1;     // sqrt(w) (A @ theta + b - mean(data))
+        qa = fma(e2, e2, fma(e0, e0, qa));
+        qb = fma(e3, e3, fma(e1, e1, qb));
     };
-    // four independent accumulator tiles per pass: a chain of dependent DMMAs alone cannot fill the pipe
     int nb = 0;
-    for (; nb + 32 <= L.np; nb += 32) {
-        double c[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    for (; nb + 32 <= L.np; nb += 32) {        // two 16-row blocks per pass
+        double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
 #pragma unroll
         for (int i = 0; i < KQ; i++) {
 #pragma unroll
-            for (int m = 0; m < 4; m++) dmma_m8n8k4(c[m][0], c[m][1], a[i], Gb[(size_t)(8 * m) * ks + 4 * i]);
+            for (int m = 0; m < 2; m++)
+                dmma_m16n8k4(c[m][0], c[m][1], c[m][2], c[m][3], Gb[(size_t)(16 * m) * ks + 4 * i],
+                             Gb[(size_t)(16 * m + 8) * ks + 4 * i], a[i]);
         }
 #pragma unroll
-        for (int m = 0; m < 4; m++) epilogue(nb + 8 * m, c[m][0], c[m][1]);
+        for (int m = 0; m < 2; m++) epilogue(nb + 16 * m, c[m][0], c[m][1], c[m][2], c[m][3]);
     }
-    for (; nb < L.np; nb += 8) {
-        double c0 = 0.0, c1 = 0.0;
+    for (; nb < L.np; nb += 16) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
 #pragma unroll
-        for (int i = 0; i < KQ; i++) dmma_m8n8k4(c0, c1, a[i], Gb[4 * i]);
-        epilogue(nb, c0, c1);
+        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, Gb[4 * i], Gb[(size_t)8 * ks + 4 * i], a[i]);
+        epilogue(nb, c0, c1, c2, c3);
     }
+    // rows are spread over the 8 lanes that share t: butterfly over g, then every lane fetches the sum of ITS chain
+    // (chain g sits in element g & 1 of the lanes with t = g >> 1)
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        qa += __shfl_xor_sync(0xffffffffu, qa, o);
+        qb += __shfl_xor_sync(0xffffffffu, qb, o);
+    }
+    const int src = (g << 2) | (g >> 1);
+    const double va = __shfl_sync(0xffffffffu, qa, src), vb = __shfl_sync(0xffffffffu, qb, src);
+    const double q = (g & 1) ? vb : va;
     double pr = 0.0;
 #pragma unroll
     for (int i = 0; i < KQ; i++) {
         const double x = a[i] - L.pmean[4 * i + t];
         pr = fma(L.pprec[4 * i + t] * x, x, pr);
     }
-    return -0.5 * (quad_sum(q) + L.q_const) + (-0.5 * quad_sum(pr));
+    return -0.5 * (q + L.q_const) + (-0.5 * quad_sum(pr));
 }
 
 constexpr int BIG_WARPS = 16;      // warps per CTA: 8 chains each, <= 128 registers per thread
@@ -139,7 +163,8 @@ constexpr int BIG_WARPS = 16;      // warps per CTA: 8 chains each, <= 128 regis
 // parity tests live in the FREE_NOISE = false instance, which keeps the step loop of the production one small
 // enough for the instruction cache (stall reason no_instruction in profiles/r01_linear_dmma.md).
 template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
-__global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh)
+__global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
+                                                                          long long *tile_done)
 {
     const int noise_mode = FREE_NOISE ? (int)YG_NOISE_PHILOX : a.noise_mode;
     extern __shared__ __align__(16) double smem[];
@@ -154,13 +179,14 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
     for (int l = 0; l < 2; l++) {
         Lv[l].G = smem + H.lvl[l].G_off;
         Lv[l].bd = smem + H.lvl[l].bd_off;
-        Lv[l].nw = smem + H.lvl[l].nw_off;
         Lv[l].pmean = smem + H.lvl[l].pmean_off;
         Lv[l].pprec = smem + H.lvl[l].pprec_off;
         Lv[l].q_const = H.lvl[l].q_const;
         Lv[l].np = H.lvl[l].np;
     }
     const double *propL = smem + H.propL_off;      // [kp] diagonal proposal factor (zero beyond dim)
+    const bool pcn = H.proposal == YG_PROPOSAL_PCN;
+    const double *pcn_mean = smem + H.pcn_mean_off;
     // current state of the warp's 8 chains: [8][ks] doubles after the problem blob; lane (g, t) only ever
     // touches its own slots (row g, columns 4 i + t), so no synchronisation is needed, and the row stride
     // (4 mod 16 doubles) makes the accesses bank-conflict free
@@ -170,20 +196,27 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
 
-    const int64_t n_tiles = (N + 7) / 8;
-    for (int64_t tile = (int64_t)blockIdx.x * BIG_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * BIG_WARPS) {
+    // ---- one piece of work: transitions [s0, s1) of the 8 chains of `tile` -------------------------------------
+    auto run_piece = [&](const int64_t tile, const int64_t s0, const int64_t s1) {
         // this lane's chain (a row beyond n_chains is computed but never stored)
         const int64_t gr = tile * 8 + g;
         const bool live = gr < N;
         const int64_t gg = live ? gr : 0;
         const uint64_t gid = (uint64_t)(a.chain_offset + gg);
+        if (s0 > 0) {      // the transitions before s0 belong to the warp that owns the preceding range: wait for its hand-over
+            if (lane == 0) {
+                while (*reinterpret_cast<volatile long long *>(tile_done + tile) != s0) __nanosleep(200);
+            }
+            __syncwarp();
+            __threadfence();
+        }
 #pragma unroll 1
         for (int i = 0; i < KQ; i++) {
             const int k = 4 * i + t;
-            TH(i) = (k < d) ? a.theta[(int64_t)k * N + gg] : 0.0;
+            TH(i) = (k < d) ? __ldcg(a.theta + (int64_t)k * N + gg) : 0.0;
         }
-        double lp0 = a.logpost[gg], lp1 = TWO_LEVEL ? a.logpost[N + gg] : 0.0;
-        unsigned long long nacc = a.n_accept[gg];
+        double lp0 = __ldcg(a.logpost + gg), lp1 = TWO_LEVEL ? __ldcg(a.logpost + N + gg) : 0.0;
+        unsigned long long nacc = __ldcg(a.n_accept + gg);
 
         // Welford (estimation.py:36-53, diagonal M2) in run-length form: a chain that stays at x for m
         // consecutive steps contributes  n' = n + m, mean' = mean + (x - mean) m / n',
@@ -191,7 +224,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
         // accumulators in (L2-resident) global memory this touches them once per accepted move
         // instead of once per step; the registers stay with the GEMM operands.  Loads of a batch of
         // columns are issued before any store (a store may alias the next load for the compiler).
-        double run = 0.0, wn = (double)a.welford_n0;
+        double run = 0.0, wn = (double)(a.welford_n0 + s0);
         auto welford_flush = [&](const bool f) {
             const bool fl = f && live && run != 0.0;
             if (!__any_sync(0xffffffffu, fl)) return;
@@ -204,8 +237,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                 for (int i = 0; i < B; i++) {
                     const int k = 4 * (i0 + i) + t;
                     const bool on = fl && k < d;
-                    m0[i] = on ? a.w_mean[(int64_t)k * N + gr] : 0.0;
-                    v0[i] = on ? a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] : 0.0;
+                    m0[i] = on ? __ldcg(a.w_mean + (int64_t)k * N + gr) : 0.0;
+                    v0[i] = on ? __ldcg(a.w_m2 + (int64_t)big_w2_index(k, d) * N + gr) : 0.0;
                 }
 #pragma unroll
                 for (int i = 0; i < B; i++) {
@@ -224,7 +257,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
         // sub-step j gives z[2b], z[2b+1].  Columns 4i+t and 4i+(t^1) of a lane pair are the two halves of
         // pair b = (4i + (t & ~1)) / 2: the even lane draws the pairs of even i, the odd lane those of odd
         // i, and they swap the halves they do not own -- one Philox block + one Box-Muller per lane and
-        // 4 parameters.
+        // 4 parameters.  pCN (pcn.py:30-35): p = sqrt(1 - 2h) s + sqrt(2h) (m + L z).
         auto propose = [&](auto &&src, int64_t n, int j, double (&p)[KQ]) {
             bool same = true;
 #pragma unroll
@@ -257,7 +290,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                 for (int e = 0; e < 2; e++) {
                     if (i2 + e < KQ) {
                         const double sv = src(i2 + e);
-                        p[i2 + e] = __dadd_rn(sv, __dmul_rn(propL[4 * (i2 + e) + t], zv[e]));
+                        const double lz = __dmul_rn(propL[4 * (i2 + e) + t], zv[e]);
+                        p[i2 + e] = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[4 * (i2 + e) + t], lz)))
+                                        : __dadd_rn(sv, lz);
                         same = same && (p[i2 + e] == sv);
                     }
                 }
@@ -267,8 +302,8 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
             return ((m >> (4 * g)) & 0xFu) == 0xFu;
         };
 
-        int64_t thin_left = a.thin, thin_out = -1;
-        for (int64_t n = 0; n < a.n_steps; n++) {
+        int64_t thin_left = a.thin - (s0 % a.thin), thin_out = s0 / a.thin - 1;      // once per piece, not per step
+        for (int64_t n = s0; n < s1; n++) {
             const uint64_t step = (uint64_t)(a.step0 + n);
             const bool store_now = (--thin_left == 0);     // (n + 1) % thin == 0 without a 64-bit division per step
             if (store_now) { thin_left = a.thin; thin_out++; }
@@ -383,6 +418,38 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                 a.n_accept[gr] = nacc;
             }
         }
+        if (s1 < a.n_steps) {       // hand the tile over to the warp that owns the following range
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile long long *>(tile_done + tile) = s1;
+        }
+    };
+
+    // ---- balanced schedule: this warp's contiguous range of the (tile-major, step-minor) work list ------------------
+    const int64_t n_tiles = (N + 7) / 8, S = a.n_steps;
+    const int64_t gw = (int64_t)blockIdx.x * BIG_WARPS + warp, GW = (int64_t)gridDim.x * BIG_WARPS;
+    // ranges in units of transitions: [lo, hi); n_tiles * S < 2^63 / GW for every admissible size
+    const int64_t U = n_tiles * S;
+    const int64_t lo = (U / GW) * gw + ((U % GW) * gw) / GW, hi = (U / GW) * (gw + 1) + ((U % GW) * (gw + 1)) / GW;
+    if (lo < hi) {
+        const int64_t t_first = lo / S, s_first = lo - t_first * S;
+        const int64_t t_last = (hi - 1) / S, s_end = hi - t_last * S;          // transitions [.., s_end) of the last tile
+        // Pieces in the order they are run (ONE call site: the step loop must not be inlined several times, it would
+        // no longer fit the instruction cache): the head of the last tile (it has no predecessor, so it can always
+        // run), the whole tiles, and last the tail of the first tile -- it waits for the previous warp's head, which
+        // that warp ran FIRST.  A range inside one tile is a single piece.
+        const bool single = t_first == t_last;
+        const int64_t has_head = (!single && s_end < S) ? 1 : 0, has_tail = (!single && s_first > 0) ? 1 : 0;
+        const int64_t w_lo = t_first + has_tail, n_whole = single ? 0 : (t_last + (s_end == S ? 1 : 0)) - w_lo;
+        const int64_t n_pieces = single ? 1 : has_head + n_whole + has_tail;
+#pragma unroll 1
+        for (int64_t q = 0; q < n_pieces; q++) {
+            int64_t tile = w_lo + (q - has_head), s0 = 0, s1 = S;
+            if (single) { tile = t_first; s0 = s_first; s1 = s_end; }
+            else if (has_head && q == 0) { tile = t_last; s1 = s_end; }
+            else if (q - has_head >= n_whole) { tile = t_first; s0 = s_first; }
+            run_piece(tile, s0, s1);
+        }
     }
 #undef TH
     // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
@@ -402,7 +469,7 @@ __global__ void big_logpost_kernel(const DevBigHeader *gh, int lvl, const double
     const DevBigHeader &H = *gh;
     const double *tail = reinterpret_cast<const double *>(gh + 1);
     const BigLevel &L = H.lvl[lvl];
-    const double *G = tail + L.G_off, *bd = tail + L.bd_off, *nw = tail + L.nw_off;
+    const double *G = tail + L.G_off, *bd = tail + L.bd_off;             // both carry sqrt(n_data * noise precision)
     const double *pm = tail + L.pmean_off, *pw = tail + L.pprec_off;
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
@@ -410,7 +477,7 @@ __global__ void big_logpost_kernel(const DevBigHeader *gh, int lvl, const double
             double f = 0.0;
             for (int k = 0; k < H.dim; k++) f = fma(G[(size_t)col * H.ks + k], theta[(int64_t)k * n + c], f);
             const double e = f + bd[col];
-            s = fma(nw[col] * e, e, s);
+            s = fma(e, e, s);
         }
         s += L.q_const;
         double p = 0.0;
@@ -451,8 +518,10 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
                     : (free_noise ? linear_dmma_mh_kernel<KQ, false, true> : linear_dmma_mh_kernel<KQ, false, false>);
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n_chains + 7) / 8;
+    // persistent grid, every CTA resident (one per SM): the balanced schedule lets warps wait on one another
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BIG_WARPS - 1) / BIG_WARPS, e->sm_count));
-    kern<<<grid, BIG_WARPS * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem));
+    YG_CUDA_CHECK(cudaMemsetAsync(e->big_done, 0, sizeof(long long) * (size_t)tiles, st));
+    kern<<<grid, BIG_WARPS * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
     e->last_block = BIG_WARPS * 32;
