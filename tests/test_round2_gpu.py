@@ -346,7 +346,7 @@ def test_iat_constant_series_reports_zero_ess():
 def test_dmma_path_normals_match_the_oracle_transform():
     """the Box-Muller transform of the tensor-path kernel runs in FP32 but from the oracle's
     uniforms (u1 = (k1 + 1) 2^-53 through log / log1p, sign bit + 52-bit angle): the device normals equal
-    cport.philox_normals (FP64 transform) to |dz| <= 4e-6 (1 + |z|), are exactly sign symmetric in construction and
+    cport.philox_normals (FP64 transform) to |dz| <= 6e-6 (1 + |z|), are exactly sign symmetric in construction and
     never give a zero radius short of u1 = 1."""
     from oracle import cport
     meta, arrays = bp.big_linear_problem(23, 45, 3)
@@ -361,7 +361,7 @@ def test_dmma_path_normals_match_the_oracle_transform():
             want = cport.philox_normals(seed, 1000 + c, n, 0, 23)
             err = np.abs(z[n, 0, :, c] - want) / (1.0 + np.abs(want))
             worst = max(worst, err.max())
-    assert worst <= 4e-6, worst
+    assert worst <= 6e-6, worst
     assert abs(z.mean()) < 0.01 and abs(z.var() - 1.0) < 0.02 and np.all(z != 0.0)
     assert abs((z > 0).mean() - 0.5) < 0.01
 

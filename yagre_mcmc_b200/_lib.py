@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyagre_b200.so")
+# YAGRE_B200_LIB: development override (an alternative build of the same library, e.g. tools/_build/...)
+LIB_PATH = os.environ.get("YAGRE_B200_LIB") or os.path.join(_HERE, "libyagre_b200.so")
 
 YG_ABI_VERSION = 4
 YG_MAX_LEVELS = 3

@@ -58,33 +58,92 @@ YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, doubl
 }
 
 // Box-Muller on one Philox block with the TRANSFORM in FP32 (the FP32 / SFU pipes are idle next to the GEMM, the
-// FP64 pipe is not).  Same uniforms as the oracle's yo_philox_normals: u1 = (k1 + 1) 2^-53 in (0, 1] and
-// u2 = k2 2^-53 in [0, 1) from the 53 high bits of the two word pairs; z = sqrt(-2 ln u1) (cos, sin)(2 pi u2).
-//   * -ln u1 keeps its relative accuracy over the whole range: for u1 > 1/2 it is -log1pf(-(1 - u1)) with
-//     1 - u1 = (2^53 - k1 - 1) 2^-53 formed exactly in integers (a float of u1 itself would round to 1 for
-//     u1 > 1 - 2^-25 and give a zero radius, i.e. a spurious "proposal == state"); the radius is zero only for
-//     u1 = 1, with probability 2^-53, exactly like the FP64 transform;
-//   * the top bit of k2 is the SIGN of (cos, sin) -- (cos, sin)(x + pi) = -(cos, sin)(x) -- and the other 52 bits
-//     the angle in [0, pi): P(z) = P(-z) holds exactly, not up to the float grid of the angle.
-// The normals equal the oracle's FP64 ones to |dz| <= 4e-6 (1 + |z|) (tests/test_round2_gpu.py); a recorded stream
-// replays bit-exactly.  Not inlined on purpose: inlined copies (Philox rounds + logf + sincospif) per proposal made
-// the step loop larger than the instruction cache (profiles/r01_linear_dmma.md).
-__device__ __noinline__ void philox_normal_pair_f32(uint64_t seed, uint64_t chain, uint64_t step, uint32_t sub, uint32_t b,
-                                                    double &z0, double &z1)
+// FP64 pipe is not).  Same uniforms as the oracle's yo_philox_normals: u1 = m1 2^-53 in (0, 1] and u2 = k2 2^-53 in
+// [0, 1) from the 53 high bits of the two word pairs; z = sqrt(-2 ln u1) (cos, sin)(2 pi u2).
+//   * BRANCH-FREE on purpose (no logf / sqrtf / sincospif: their slow paths are branches): the transform is inlined
+//     into the GEMM loop of the preceding evaluation and must share a basic block with the DMMAs for the scheduler
+//     to interleave the two instruction streams;
+//   * -ln u1 keeps its RELATIVE accuracy over the whole range: u1 = m 2^e with m in [0.75, 1.5), ln m = 2 atanh(s),
+//     s = (m - 1) / (m + 1), and for u1 >= 0.75 the numerator m - 1 = -(1 - u1) is formed exactly in integers,
+//     (2^53 - m1) 2^-53 (a float of u1 itself would round to 1 for u1 > 1 - 2^-25 and give a zero radius, i.e. a
+//     spurious "proposal == state"); the radius is zero only for u1 = 1, probability 2^-53, like the FP64 transform;
+//   * the top bit of k2 is the SIGN of (cos, sin) -- (cos, sin)(x + pi) = -(cos, sin)(x) -- and the other 52 bits the
+//     angle in [0, pi): P(z) = P(-z) holds exactly, not up to the float grid of the angle.
+// The normals equal the oracle's FP64 ones to |dz| <= 6e-6 (1 + |z|) (tests/test_round2_gpu.py: MUFU sine / cosine
+// have an absolute error of 2^-21.4); a recorded stream replays bit-exactly.
+YG_DEVFN float neg_log_u53(const uint64_t m1)        // -ln(m1 2^-53), m1 in [1, 2^53]
 {
-    const uint4 w = philox_block(seed, chain, step, sub, b);
-    const uint64_t m1 = ((((uint64_t)w.x << 32) | w.y) >> 11) + 1ull;          // [1, 2^53]: u1 = m1 2^-53
-    const uint64_t k2 = (((uint64_t)w.z << 32) | w.w) >> 11;                   // [0, 2^53): u2 = k2 2^-53
-    float nl;                                                                   // -ln u1 >= 0
-    if (m1 > (1ull << 52)) nl = -log1pf(-((float)((1ull << 53) - m1) * 0x1.0p-53f));
-    else nl = -logf((float)m1 * 0x1.0p-53f);
-    const float R = sqrtf(2.0f * nl);
-    float sn, cs;
-    sincospif((float)(k2 & ((1ull << 52) - 1ull)) * 0x1.0p-52f, &sn, &cs);      // 2 pi u2 = pi (top bit) + pi (low bits) 2^-52
-    const float sg = (k2 >> 52) ? -R : R;
-    z0 = (double)(sg * cs);
-    z1 = (double)(sg * sn);
+    const float t = (float)((1ull << 53) - m1) * 0x1.0p-53f;                   // 1 - u1, relative accuracy 2^-24
+    const float x = (float)m1 * 0x1.0p-53f;                                    // u1 in [2^-53, 1]: a normal float
+    const int bits = __float_as_int(x);
+    int e = ((bits >> 23) & 0xff) - 127;
+    float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);                // [1, 2)
+    const bool up = m >= 1.5f;
+    m = up ? 0.5f * m : m;                                                     // [0.75, 1.5)
+    e += up ? 1 : 0;
+    const float dm = (e == 0) ? -t : m - 1.0f;                                 // m - 1 (exact for the float m)
+    const float s = __fdividef(dm, 2.0f + dm), s2 = s * s;                     // |s| <= 1/5
+    float P = fmaf(s2, 1.0f / 11.0f, 1.0f / 9.0f);
+    P = fmaf(s2, P, 1.0f / 7.0f);
+    P = fmaf(s2, P, 0.2f);
+    P = fmaf(s2, P, 1.0f / 3.0f);
+    P = fmaf(s2, P, 1.0f);
+    return -fmaf((float)e, 0.693147180559945309f, 2.0f * s * P);
 }
+
+// The same transform cut into 13 micro-steps (10 Philox rounds, radius, angle, store) that logpost_tile spreads over
+// the k-steps of one pass of its GEMM loop: ptxas keeps the order of the PTX it is given, so the interleaving has to
+// be written out -- a block of noise code placed before the DMMAs of a pass is executed before them, not under them.
+struct NoiseSlice {
+    uint4 c;
+    uint2 k;
+    float R;
+    float2 z;
+    float2 *dst;
+    bool on;
+    YG_DEVFN void begin(uint64_t seed, uint64_t chain, uint64_t step, uint32_t sub, uint32_t b, float2 *dst_, bool on_)
+    {
+        k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        c = make_uint4((uint32_t)chain, (uint32_t)step, (uint32_t)(step >> 32),
+                       (uint32_t)(((chain >> 32) & 0xFFu) << 24) | (sub << 8) | b);       // philox_block's counter
+        dst = dst_;
+        on = on_;
+    }
+    YG_DEVFN void micro(const int u)
+    {
+        if (u < 10) {                                            // one Philox4x32 round (common.cuh:philox4x32_10)
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += 0x9E3779B9u;
+            k.y += 0xBB67AE85u;
+        } else if (u == 10) {
+            const uint64_t m1 = ((((uint64_t)c.x << 32) | c.y) >> 11) + 1ull;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(2.0f * neg_log_u53(m1)));
+        } else if (u == 11) {
+            const uint64_t k2 = (((uint64_t)c.z << 32) | c.w) >> 11;
+            float sn, cs;
+            __sincosf(3.14159265358979324f * ((float)(k2 & ((1ull << 52) - 1ull)) * 0x1.0p-52f), &sn, &cs);
+            const float sg = (k2 >> 52) ? -R : R;
+            z = make_float2(sg * cs, sg * sn);
+        } else if (u == 12) {
+            if (on) *dst = z;
+        }
+    }
+    // k-step i of KQ: its share of the 13 micro-steps
+    template <int KQ>
+    YG_DEVFN void stage(const int i)
+    {
+#pragma unroll
+        for (int u = 0; u < 13; u++)
+            if (u >= (13 * i) / KQ && u < (13 * (i + 1)) / KQ) micro(u);
+    }
+    YG_DEVFN void all()
+    {
+#pragma unroll
+        for (int u = 0; u < 13; u++) micro(u);
+    }
+};
 
 YG_DEVFN double quad_sum(double v)
 {
@@ -104,8 +163,16 @@ struct SmemLevel {
 
 // log-posterior of the chain (column g of the warp's d x 8 tile) whose parameters are spread over the quad:
 // a[i] = theta[4 i + t].  Every lane of a quad returns the same value.
-template <int KQ>
-YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)[KQ], const int g, const int t)
+// side.begin(pass) is called at the start of every pass over 32 (or the last 16) data rows and side.stage(i) after
+// k-step i of the pass: independent work written out between the DMMAs (the noise of the NEXT proposal; SideNone
+// for the evaluations that have none to draw).
+struct SideNone {
+    YG_DEVFN void begin(int) {}
+    YG_DEVFN void stage(int) {}
+};
+
+template <int KQ, typename SIDE>
+YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)[KQ], const int g, const int t, SIDE &&side)
 {
     // sum_rows ||F - d_row||^2_P = sum_col w_col (F_col - mean_col)^2 + q_const  (exact identity; no cancellation:
     // the row scatter is a precomputed constant).  Accumulator layout of m16n8k4 with G as the A operand:
@@ -117,16 +184,18 @@ YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)
         qa = fma(e2, e2, fma(e0, e0, qa));
         qb = fma(e3, e3, fma(e1, e1, qb));
     };
-    int nb = 0;
+    int nb = 0, pass = 0;
     for (; nb + 32 <= L.np; nb += 32) {        // two 16-row blocks per pass
         double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+        side.begin(pass++);
 #pragma unroll
         for (int i = 0; i < KQ; i++) {
 #pragma unroll
             for (int m = 0; m < 2; m++)
                 dmma_m16n8k4(c[m][0], c[m][1], c[m][2], c[m][3], Gb[(size_t)(16 * m) * ks + 4 * i],
                              Gb[(size_t)(16 * m + 8) * ks + 4 * i], a[i]);
+            side.stage(i);
         }
 #pragma unroll
         for (int m = 0; m < 2; m++) epilogue(nb + 16 * m, c[m][0], c[m][1], c[m][2], c[m][3]);
@@ -134,8 +203,12 @@ YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)
     for (; nb < L.np; nb += 16) {
         double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+        side.begin(pass++);
 #pragma unroll
-        for (int i = 0; i < KQ; i++) dmma_m16n8k4(c0, c1, c2, c3, Gb[4 * i], Gb[(size_t)8 * ks + 4 * i], a[i]);
+        for (int i = 0; i < KQ; i++) {
+            dmma_m16n8k4(c0, c1, c2, c3, Gb[4 * i], Gb[(size_t)8 * ks + 4 * i], a[i]);
+            side.stage(i);
+        }
         epilogue(nb, c0, c1, c2, c3);
     }
     // rows are spread over the 8 lanes that share t: butterfly over g, then every lane fetches the sum of ITS chain
@@ -157,13 +230,23 @@ YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)
     return -0.5 * (q + L.q_const) + (-0.5 * quad_sum(pr));
 }
 
-constexpr int BIG_WARPS = 16;      // warps per CTA: 8 chains each, <= 128 registers per thread
+constexpr int BIG_WARPS = 16;      // most warps per CTA (8 chains each, <= 128 registers per thread); fewer when shared memory is short
+// d > 32 (KQ = 16): G of a 256-row model leaves shared memory for 13 warps; 12 are used -- three per sub-partition may
+// take 168 registers each (a fourth warp on one sub-partition caps everybody at 128: the register file is per
+// sub-partition), which the 64-parameter operand tiles need: no spills, 25.2 against 20.7 TFLOP/s with 13 x 128.
+#ifndef YG_BIG_WARPS_KQ16
+#define YG_BIG_WARPS_KQ16 12
+#endif
+__host__ __device__ constexpr int big_max_warps(int kq) { return kq == 16 ? YG_BIG_WARPS_KQ16 : BIG_WARPS; }
+// per-warp shared memory: the state tile [8][ks] doubles and the noise tile [8][4 KQ + 4] floats of the next proposal
+__host__ __device__ constexpr int big_zs(int kq) { return 4 * kq + 4; }
+inline size_t big_warp_bytes(int ks, int kq) { return sizeof(double) * 8 * (size_t)ks + sizeof(float) * 8 * (size_t)big_zs(kq); }
 
 // FREE_NOISE = true: the production instance (Philox noise only).  The injected / recorded noise paths of the
 // parity tests live in the FREE_NOISE = false instance, which keeps the step loop of the production one small
 // enough for the instruction cache (stall reason no_instruction in profiles/r01_linear_dmma.md).
 template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
-__global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
+__global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
                                                                           long long *tile_done)
 {
     const int noise_mode = FREE_NOISE ? (int)YG_NOISE_PHILOX : a.noise_mode;
@@ -191,7 +274,10 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
     // touches its own slots (row g, columns 4 i + t), so no synchronisation is needed, and the row stride
     // (4 mod 16 doubles) makes the accesses bank-conflict free
     const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
-    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * 8 * ks;
+    constexpr int ZS = big_zs(KQ);
+    const int n_warps = blockDim.x >> 5;
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks + 4 * ZS);       // 8 ZS floats = 4 ZS doubles
+    float *zb = reinterpret_cast<float *>(ths + 8 * ks);
 #define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
@@ -253,54 +339,72 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
             if (fl) { wn += run; run = 0.0; }
         };
 
-        // p = s + L z with a diagonal L, unfused like numpy; z keyed like the per-thread kernels: pair b of
-        // sub-step j gives z[2b], z[2b+1].  Columns 4i+t and 4i+(t^1) of a lane pair are the two halves of
-        // pair b = (4i + (t & ~1)) / 2: the even lane draws the pairs of even i, the odd lane those of odd
-        // i, and they swap the halves they do not own -- one Philox block + one Box-Muller per lane and
-        // 4 parameters.  pCN (pcn.py:30-35): p = sqrt(1 - 2h) s + sqrt(2h) (m + L z).
+        // Noise of proposal (n, j): pair b of the sub-step gives z[2b], z[2b+1], keyed like the per-thread kernels.
+        // Columns 4i+t and 4i+(t^1) of a lane pair are the two halves of pair b = (4i + (t & ~1)) / 2: the even lane
+        // draws the pairs of even i, the odd lane those of odd i -- one Philox block + one Box-Muller per lane and 4
+        // parameters -- and both halves go to the warp's noise tile, from where every lane later picks its columns.
+        // Slice `it` (of KQ / 2) is one pair per lane; the slices are drawn INSIDE the GEMM loop of the evaluation that
+        // precedes the proposal (the noise does not depend on the chain state: counter-based Philox).
+        NoiseSlice ns;
+        auto slice_begin = [&](const int64_t n, const int j, const int it, const bool on) {
+            // a slice index beyond KQ / 2 (more passes than slices) redraws an earlier slice: same values, same place
+            const int i_mine = 2 * (it & (KQ / 2 - 1)) + odd;
+            ns.begin(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)((4 * i_mine + (t & ~1)) >> 1),
+                     reinterpret_cast<float2 *>(zb + g * ZS + 4 * i_mine + (t & ~1)), on && noise_mode != YG_NOISE_INJECT);
+        };
+        auto gen_noise = [&](const int64_t n, const int j, const int it) {       // one slice, not interleaved with anything
+            slice_begin(n, j, it, true);
+            ns.all();
+        };
+        struct SideNoise {
+            decltype(slice_begin) &sb;
+            NoiseSlice &ns;
+            int64_t n;
+            int j;
+            bool on;
+            YG_DEVFN void begin(const int pass) { sb(n, j, pass, on); }
+            YG_DEVFN void stage(const int i) { ns.template stage<KQ>(i); }
+        };
+        // the proposal after (n, j) in the order the chain consumes them; n == s1 means "none in this piece"
+        auto next_of = [&](int64_t &n, int &j) {
+            if (++j == J) { j = 0; n++; }
+        };
+        // p = s + L z with a diagonal L, unfused like numpy.  pCN (pcn.py:30-35): p = sqrt(1 - 2h) s + sqrt(2h) (m + L z).
         auto propose = [&](auto &&src, int64_t n, int j, double (&p)[KQ]) {
             bool same = true;
+            __syncwarp();                                  // the noise tile was written by other lanes
 #pragma unroll
-            for (int i2 = 0; i2 < KQ; i2 += 2) {
-                double zv[2] = {0.0, 0.0};                 // z of columns 4 i2 + t and 4 (i2 + 1) + t
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                double zv = 0.0;
                 if (noise_mode == YG_NOISE_INJECT) {
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int k = 4 * (i2 + e) + t;
-                        if (k < d && i2 + e < KQ) zv[e] = a.z[((n * J + j) * d + k) * N + gg];
-                    }
-                } else {
-                    const int i_mine = i2 + odd;           // the i whose pair this lane draws
-                    double z0, z1;
-                    philox_normal_pair_f32(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j,
-                                           (uint32_t)((4 * i_mine + (t & ~1)) >> 1), z0, z1);
-                    // even lane keeps z0 of its pair (column 4 i2 + t), needs z0 of the odd lane's pair (i2 + 1);
-                    // odd lane keeps z1 of its pair (column 4 (i2+1) + t), needs z1 of the even lane's pair (i2)
-                    const double recv = __shfl_xor_sync(0xffffffffu, odd ? z0 : z1, 1);
-                    zv[0] = odd ? recv : z0;
-                    zv[1] = odd ? z1 : recv;
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int k = 4 * (i2 + e) + t;
-                        if (k >= d || i2 + e >= KQ) zv[e] = 0.0;
-                        else if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[e];
-                    }
+                    if (k < d) zv = a.z[((n * J + j) * d + k) * N + gg];
+                } else if (k < d) {
+                    zv = (double)zb[g * ZS + k];
+                    if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv;
                 }
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if (i2 + e < KQ) {
-                        const double sv = src(i2 + e);
-                        const double lz = __dmul_rn(propL[4 * (i2 + e) + t], zv[e]);
-                        p[i2 + e] = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[4 * (i2 + e) + t], lz)))
-                                        : __dadd_rn(sv, lz);
-                        same = same && (p[i2 + e] == sv);
-                    }
-                }
+                const double sv = src(i);
+                const double lz = __dmul_rn(propL[k], zv);
+                p[i] = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[k], lz))) : __dadd_rn(sv, lz);
+                same = same && (p[i] == sv);
             }
+            __syncwarp();                                  // every lane has read its columns: the tile may be refilled
             // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
             const unsigned m = __ballot_sync(0xffffffffu, same);
             return ((m >> (4 * g)) & 0xFu) == 0xFu;
         };
+        // log-posterior of proposal (n, j) on level 0 while the noise of the following proposal is drawn
+        auto eval_and_draw = [&](const double (&p)[KQ], int64_t n, int j) {
+            next_of(n, j);
+            const bool more = n < s1;
+            if (!more) n = s1 - 1;                                                 // a valid counter; nothing is stored
+            const double lp = logpost_tile<KQ>(Lv[0], ks, p, g, t, SideNoise{slice_begin, ns, n, j, more});
+            const int passes = (Lv[0].np + 31) >> 5;
+            if (more)
+                for (int it = passes; it < KQ / 2; it++) gen_noise(n, j, it);       // few data rows: the rest of the slices
+            return lp;
+        };
+        for (int it = 0; it < KQ / 2; it++) gen_noise(s0, 0, it);                 // the first proposal of the piece
 
         int64_t thin_left = a.thin - (s0 % a.thin), thin_out = s0 / a.thin - 1;      // once per piece, not per step
         for (int64_t n = s0; n < s1; n++) {
@@ -314,7 +418,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
             if (!TWO_LEVEL) {
                 double p[KQ];
                 const bool eq = propose([&](int i) { return TH(i); }, n, 0, p);
-                const double lpp = logpost_tile<KQ>(Lv[0], ks, p, g, t);
+                const double lpp = eval_and_draw(p, n, 0);
                 if (!eq) {                                              // metropolisHastings.py:60-61
                     if (t == 0 && live) cnt_ev0++;
                     double u;
@@ -337,7 +441,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                 for (int i = 0; i < KQ; i++) s[i] = TH(i);
                 for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
                     const bool eq = propose([&](int i) { return s[i]; }, n, j, p);
-                    const double lpp = logpost_tile<KQ>(Lv[0], ks, p, g, t);
+                    const double lpp = eval_and_draw(p, n, j);
                     if (eq) continue;
                     if (t == 0 && live) cnt_ev0++;
                     const int64_t ui = (n * J + j) * N + gg;
@@ -363,7 +467,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
                 const bool moved = (((m >> (4 * g)) & 0xFu) != 0xFu) && live;
                 double lpf = 0.0;
                 if (__any_sync(0xffffffffu, moved)) {
-                    lpf = logpost_tile<KQ>(Lv[1], ks, s, g, t);
+                    lpf = logpost_tile<KQ>(Lv[1], ks, s, g, t, SideNone{});
                     if (moved) {
                         if (t == 0) cnt_ev1++;
                         double u;
@@ -427,7 +531,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, 1) linear_dmma_mh_kernel(const
 
     // ---- balanced schedule: this warp's contiguous range of the (tile-major, step-minor) work list ------------------
     const int64_t n_tiles = (N + 7) / 8, S = a.n_steps;
-    const int64_t gw = (int64_t)blockIdx.x * BIG_WARPS + warp, GW = (int64_t)gridDim.x * BIG_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * n_warps + warp, GW = (int64_t)gridDim.x * n_warps;
     // ranges in units of transitions: [lo, hi); n_tiles * S < 2^63 / GW for every admissible size
     const int64_t U = n_tiles * S;
     const int64_t lo = (U / GW) * gw + ((U % GW) * gw) / GW, hi = (U / GW) * (gw + 1) + ((U % GW) * (gw + 1)) / GW;
@@ -511,7 +615,15 @@ template <int KQ>
 int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
-    const size_t smem = sizeof(double) * ((((size_t)hh->tail_len + 1) & ~size_t(1)) + (size_t)BIG_WARPS * 8 * hh->ks);
+    // warps per CTA: as many as the shared memory left by the problem blob holds (13 at d = 64 x 256, else 16)
+    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1)), per_warp = big_warp_bytes(hh->ks, KQ);
+    const size_t budget = 227 * 1024;
+    int warps = blob < budget ? (int)std::min<size_t>(big_max_warps(KQ), (budget - blob) / per_warp) : 0;
+    if (warps < 4) {
+        yg_set_error("large linear model: %zu bytes of G / data leave no room for the per-warp tiles", blob);
+        return YG_ERR_UNSUPPORTED;
+    }
+    const size_t smem = blob + (size_t)warps * per_warp;
     const bool free_noise = a.noise_mode == YG_NOISE_PHILOX;
     auto kern = e->cfg.n_levels == 2
                     ? (free_noise ? linear_dmma_mh_kernel<KQ, true, true> : linear_dmma_mh_kernel<KQ, true, false>)
@@ -519,12 +631,12 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n_chains + 7) / 8;
     // persistent grid, every CTA resident (one per SM): the balanced schedule lets warps wait on one another
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + BIG_WARPS - 1) / BIG_WARPS, e->sm_count));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + warps - 1) / warps, e->sm_count));
     YG_CUDA_CHECK(cudaMemsetAsync(e->big_done, 0, sizeof(long long) * (size_t)tiles, st));
-    kern<<<grid, BIG_WARPS * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done);
+    kern<<<grid, warps * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
-    e->last_block = BIG_WARPS * 32;
+    e->last_block = warps * 32;
     e->last_smem = (int)smem;
     e->launches += 1;
     return YG_OK;
