@@ -10,6 +10,6 @@ ens = ChainEnsemble(LoweredProblem(meta, arrays), nc, seed=1)
 mean, _ = bp.linear_gaussian_posterior(arrays, 0)
 ens.set_state(np.tile(mean, (nc, 1)))
 for _ in range(3):
-    ens.run(10, samples=False)
+    ens.run(int(os.environ.get("STEPS", "10")), samples=False)
 torch.cuda.synchronize()
 print("ok", ens.counters())

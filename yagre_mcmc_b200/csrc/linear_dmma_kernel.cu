@@ -145,6 +145,19 @@ struct NoiseSlice {
     }
 };
 
+// Shared-memory load of a GEMM operand that ptxas may not move across its neighbours.  Left to itself ptxas gathers the
+// DMMAs of one accumulator into one dependent chain (whatever the order of the PTX), and a DMMA that waits for its
+// predecessor issues every 26 cycles instead of every 16.  Volatile loads keep their program order, so the operands of
+// k-step i + 1 of ALL accumulator chains are fetched before the DMMAs of k-step i: gathering a chain would mean
+// keeping every other chain's operands alive in registers, and the scheduler keeps the interleaved order instead
+// (SASS: DMMA R28 / R32 / R36 / R24 round robin; profiles/r02_linear_dmma.md).
+YG_DEVFN double lds_ordered(const double *p)
+{
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 YG_DEVFN double quad_sum(double v)
 {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -185,28 +198,47 @@ YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)
         qb = fma(e3, e3, fma(e1, e1, qb));
     };
     int nb = 0, pass = 0;
-    for (; nb + 32 <= L.np; nb += 32) {        // two 16-row blocks per pass
+    for (; nb + 32 <= L.np; nb += 32) {        // two 16-row blocks per pass = four interleaved DMMA.8x8x4 chains
         double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
         side.begin(pass++);
+        double A[2][2], An[2][2];
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            A[m][0] = lds_ordered(Gb + (size_t)(16 * m) * ks);
+            A[m][1] = lds_ordered(Gb + (size_t)(16 * m + 8) * ks);
+        }
 #pragma unroll
         for (int i = 0; i < KQ; i++) {
+            if (i + 1 < KQ) {
 #pragma unroll
-            for (int m = 0; m < 2; m++)
-                dmma_m16n8k4(c[m][0], c[m][1], c[m][2], c[m][3], Gb[(size_t)(16 * m) * ks + 4 * i],
-                             Gb[(size_t)(16 * m + 8) * ks + 4 * i], a[i]);
+                for (int m = 0; m < 2; m++) {
+                    An[m][0] = lds_ordered(Gb + (size_t)(16 * m) * ks + 4 * (i + 1));
+                    An[m][1] = lds_ordered(Gb + (size_t)(16 * m + 8) * ks + 4 * (i + 1));
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 2; m++) dmma_m16n8k4(c[m][0], c[m][1], c[m][2], c[m][3], A[m][0], A[m][1], a[i]);
+#pragma unroll
+            for (int m = 0; m < 2; m++) { A[m][0] = An[m][0]; A[m][1] = An[m][1]; }
             side.stage(i);
         }
 #pragma unroll
         for (int m = 0; m < 2; m++) epilogue(nb + 16 * m, c[m][0], c[m][1], c[m][2], c[m][3]);
     }
-    for (; nb < L.np; nb += 16) {
+    for (; nb < L.np; nb += 16) {              // last 16 rows: two chains
         double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
         const double *Gb = L.G + (size_t)(nb + g) * ks + t;
         side.begin(pass++);
+        double A0 = lds_ordered(Gb), A1 = lds_ordered(Gb + (size_t)8 * ks), B0 = 0.0, B1 = 0.0;
 #pragma unroll
         for (int i = 0; i < KQ; i++) {
-            dmma_m16n8k4(c0, c1, c2, c3, Gb[4 * i], Gb[(size_t)8 * ks + 4 * i], a[i]);
+            if (i + 1 < KQ) {
+                B0 = lds_ordered(Gb + 4 * (i + 1));
+                B1 = lds_ordered(Gb + (size_t)8 * ks + 4 * (i + 1));
+            }
+            dmma_m16n8k4(c0, c1, c2, c3, A0, A1, a[i]);
+            A0 = B0; A1 = B1;
             side.stage(i);
         }
         epilogue(nb, c0, c1, c2, c3);
