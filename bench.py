@@ -593,6 +593,27 @@ def measure_other_configs(device, fp64_peak, main_value, hbm_peak_gbs):
     ms, c = timed(ens, 20)
     out["C4_lv_single_level_adaptive_65536"] = lv_entry(meta, ms, c, "lv_mh_kernel<false>, per-chain adaptive Metropolis")
     ens.close()
+    # ESS/s of C4 (example_inference_lotkaVolterra_singleLevel.py: 0.15 I proposal, acceptance 0.11) against the same
+    # chains with the per-chain adaptive proposal: 16,384 chains x 2,000 transitions, burn-in 400 (adaptation included
+    # in the time), IAT on the device
+    from yagre_mcmc_b200.ensemble import iat_ess
+    c4 = {}
+    for label, ad in (("fixed_0.15I", None), ("adaptive", dict(idle=50, collection=300, eps=1e-8, refresh=10))):
+        ens = ChainEnsemble(LoweredProblem(meta, arrays), 16384, device=device, seed=6, adaptive=ad)
+        ens.set_state(bp.lv_initial_states(16384))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        smp = ens.run(2000, samples=True)["samples"]
+        e1.record()
+        torch.cuda.synchronize()
+        iat, ess_c = iat_ess(smp[400:], "max")
+        c4[label] = {"ess_per_s": float(ess_c.sum().item()) / (e0.elapsed_time(e1) * 1e-3), "mean_iat_max": float(iat.double().mean().item()),
+                     "degenerate_chains": int((ess_c == 0).sum().item()),
+                     "chain_steps_per_s": 16384 * 2000 / (e0.elapsed_time(e1) * 1e-3)}
+        del smp
+        ens.close()
+    c4["adaptive_over_fixed"] = c4["adaptive"]["ess_per_s"] / c4["fixed_0.15I"]["ess_per_s"]
+    out["C4_ess_16384x2000"] = c4
     meta, arrays = bp.lv_problem(True)
     ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5)
     ens.set_state(bp.lv_initial_states(65536))

@@ -12,7 +12,7 @@ meta, arrays = bp.lv_problem(two, Nc=Nc, Nf=Nf)
 pb = LoweredProblem(meta, arrays)
 n_chains, S = 65536, 20
 names = ["owners", "wait1", "noise", "eval", "wait2", "commit"]
-for bps, thr, seg in [(1, 1024, 128)]:
+for bps, thr, seg in [(1, int(os.environ.get("THR", 768)), 128)]:
     ens = ChainEnsemble(pb, n_chains, seed=1, blocks_per_sm=bps, threads_per_block=thr, rk4_segment=seg)
     ens.set_state(bp.lv_initial_states(n_chains))
     ens.run(100, samples=False)
@@ -29,12 +29,12 @@ for bps, thr, seg in [(1, 1024, 128)]:
     torch.cuda.synchronize()
     grid = ens.last_launch()["grid"]
     nw = thr // 32
-    t = out["samples"].view(torch.int64).flatten()[:10 * nw * grid].cpu().numpy().reshape(grid, nw, 10).astype(np.float64)
+    t = out["samples"].view(torch.int64).flatten()[:10 * 32 * grid].cpu().numpy().reshape(grid, 32, 10)[:, :nw].astype(np.float64)   # the kernel reserves 32 warp slots per CTA
     total = t[:, :, 8]
     print(f"bps={bps} thr={thr} seg={seg}: CTA total cycles mean {total.mean():.4e} min {total.min():.4e} max {total.max():.4e}")
     for k, nm in enumerate(names):
         f = t[:, :, k] / total
-        print(f"  {nm:7s} share of CTA time: mean over warps {f.mean():.4f}  warp0-13 {f[:, :14].mean():.4f}  warp14-31 {f[:, 14:].mean():.4f}  min {f.min():.4f} max {f.max():.4f}")
+        print(f"  {nm:7s} share of CTA time: mean over warps {f.mean():.4f}  first half {f[:, :nw // 2].mean():.4f}  second half {f[:, nw // 2:].mean():.4f}  min {f.min():.4f} max {f.max():.4f}")
     items_c, items_f = t[:, 0, 6], t[:, 0, 7]
     if not two:
         items_c, items_f = np.zeros_like(items_c), items_c
