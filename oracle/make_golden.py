@@ -366,6 +366,60 @@ def case_pcn_big_linear():
     save("pcn_linear_big", meta, arrays)
 
 
+def _spd(rng, d, scale):
+    A = rng.standard_normal((d, d))
+    return scale * (A @ A.T / d + 0.5 * np.eye(d))
+
+
+def case_big_linear_dense():
+    """GEMM-sized linear model with DenseCovarianceMatrix objects (statistics/covariance.py:69-94) as the proposal
+    covariance and as the prior covariance: MRW, and pCN (whose proposal factor is the dense prior's)."""
+    from yagremcmc.chain.target import UnnormalisedPosterior
+    p = big_linear_problem(d=12, dataDim=20, nData=2, seed=6)
+    d, dd = p['d'], p['dataDim']
+    rng = Generator(Philox(1395))
+    propCov, priorCov = _spd(rng, d, 0.004), _spd(rng, d, 1.5)
+    nChains, nSteps = 3, 150
+    for kind in ('mrw', 'pcn'):
+        z, u_c, u_f = make_noise(rng, nChains, nSteps, 1, d, zero_at=[(0, 6, 0)])
+        theta0 = p['truth'] + 0.05 * rng.standard_normal((nChains, d))
+        traj, acc, lp = [], [], []
+        for c in range(nChains):
+            data = rh.Data(p['data'])
+            noise = rh.CentredGaussianNoise(rh.IIDCovarianceMatrix(dd, p['noiseVar']))
+            lik = rh.AdditiveGaussianNoiseLikelihood(data, rh.ForwardModel(rh.LinearSolver(p['G_f'], p['b_f'])), noise)
+            priorMean = np.zeros(d) if kind == 'pcn' else p['priorMean']
+            prior = rh.Gaussian(rh.ParameterVector(priorMean), rh.DenseCovarianceMatrix(priorCov))
+            inj = rh.NoiseInjector(z[c], None, u_f[c])
+            if kind == 'mrw':
+                b = rh.MRWBuilder()
+                b.proposalCovariance = rh.DenseCovarianceMatrix(propCov)
+            else:
+                b = rh.PCNBuilder()
+                b.stepSize = 0.002
+            b.bayesModel = rh.BayesianRegressionModel(lik, prior)
+            mcmc = rh.quiet(b.build_method)
+            t, a = rh.run_reference_chain(mcmc, rh.ParameterVector(theta0[c].copy()), nSteps, inj, False)
+            traj.append(t); acc.append(a)
+            tgt = lik if kind == 'pcn' else UnnormalisedPosterior(lik, prior)
+            lp.append(logpost_along(tgt, rh.ParameterVector, t))
+            print(f"    {kind}_linear_big_dense chain {c}: acceptance {a.mean():.3f}")
+        prec = np.linalg.inv(priorCov)
+        arrays = dict(theta0=theta0, z=z, u_c=u_c, u_f=u_f, traj=traj, accepted=acc, logpost_L0=lp,
+                      L0_data=p['data'], L0_noise_prec=diag_precision(p['noiseVar'], dd), L0_G=p['G_f'], L0_b=p['b_f'])
+        if kind == 'mrw':
+            arrays.update(prop_L=lower_proposal('dense', propCov, d), L0_prior_mean=p['priorMean'],
+                          L0_prior_prec=0.5 * (prec + prec.T))
+            meta = dict(model='linear', dim=d, levels=1, J=1, eq='exact',
+                        note='GEMM-sized linear model (d=12, dataDim=20, nData=2), dense proposal covariance and dense Gaussian prior')
+        else:
+            arrays.update(prop_L=lower_proposal('dense', priorCov, d), pcn_mean=np.zeros(d), L0_prior_mean=np.zeros(d),
+                          L0_prior_prec=np.zeros((d, d)))
+            meta = dict(model='linear', dim=d, levels=1, J=1, eq='exact', proposal='pcn', pcn_step=0.002,
+                        note='pCN on a GEMM-sized linear model with a dense centred Gaussian prior')
+        save(f"{kind}_linear_big_dense", meta, arrays)
+
+
 # --------------------------------------------------------------------------
 # Lotka-Volterra (C4 / C5)
 # --------------------------------------------------------------------------
@@ -954,6 +1008,7 @@ if __name__ == "__main__":
     if want('biglinear2'):
         case_big_linear(False, name="mrw_linear_big_rows12", d=10, dataDim=33, nData=12, seed=4)     # more than 8 data rows
         case_pcn_big_linear()
+        case_big_linear_dense()
     if want('post'):
         case_postprocessing()
     if want('lv'):

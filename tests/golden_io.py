@@ -9,7 +9,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CHAIN_CASES = ["mrw_gauss1d", "mrw_gauss2d_iid", "mrw_gauss2d_diag", "mrw_gauss2d_dense",
                "mlda_gauss2d", "mrw_linear", "mlda_linear", "mrw_lv", "mlda_lv", "mlda_lv_nonfinite",
                "pcn_lv", "pcn_linear_dense", "mrw_linear_big", "mlda_linear_big",
-               "mrw_linear_big_rows12", "pcn_linear_big"]
+               "mrw_linear_big_rows12", "pcn_linear_big", "mrw_linear_big_dense", "pcn_linear_big_dense"]
 # MLDA with two surrogates as the reference runs it (mlda.py:12-43,60-71,112-117)
 MLDA3_CASES = ["mlda3_gauss2d", "mlda3_gauss2d_hier", "mlda3_linear"]
 # TemperedUnnormalisedPosterior surrogate (chain/target.py:25-43)

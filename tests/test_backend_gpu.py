@@ -253,10 +253,14 @@ def test_big_linear_posterior_moments_and_diagnostics():
     # sizes beyond the kernel, or features it does not have, are refused loudly
     with pytest.raises(NotImplementedError):
         _ens(*bp.big_linear_problem(65, 64, 1), 16)
-    bad = dict(arrays)
-    bad["prop_L"] = np.linalg.cholesky(np.eye(d) + 0.01)
-    with pytest.raises(NotImplementedError):
-        _ens(meta, bad, 16)
+    dense = dict(arrays)                            # round 2: a dense proposal factor runs (4 warps per SM at this size)
+    dense["prop_L"] = 0.02 * np.linalg.cholesky(np.eye(d) + 0.01)
+    e2 = _ens(meta, dense, 64, seed=1)
+    e2.set_state(np.tile(mean, (64, 1)))
+    e2.run(20, samples=False)
+    assert e2.counters()["transitions"] == 64 * 20 and e2.last_launch()["block"] == 4 * 32
+    with pytest.raises(NotImplementedError):        # per-chain adaptation would need a d x d factor per chain
+        _ens(meta, arrays, 16, adaptive=dict(idle=1, collection=2))
 
 
 def test_logpost_matches_oracle():

@@ -135,12 +135,17 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
             yg_set_error("large linear model: tempered levels are not implemented");
             return YG_ERR_UNSUPPORTED;
         }
-    if (!is_diagonal(pb->prop_L, d)) {
-        yg_set_error("large linear model: the proposal factor must be diagonal");
-        return YG_ERR_UNSUPPORTED;
-    }
+    const bool dense_L = !is_diagonal(pb->prop_L, d);
+    for (int i = 0; i < d; i++)
+        for (int j = i + 1; j < d; j++)
+            if (pb->prop_L[(size_t)i * d + j] != 0.0) {
+                yg_set_error("prop_L must be lower triangular");
+                return YG_ERR_INVALID;
+            }
     const int kp = d <= 16 ? 16 : (d <= 32 ? 32 : 64), ks = kp + 4;
     size_t tail_len = 0;
+    bool dense_prior[2] = {false, false};
+    std::vector<double> Rp[2];            // chol(prior precision)' of the levels with a dense prior
     for (int l = 0; l < nl; l++) {
         const yg_level &L = pb->level[l];
         if (!L.data || !L.noise_prec || !L.prior_mean || !L.prior_prec || !L.G || !L.b || L.n_data < 1 ||
@@ -152,8 +157,8 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
             yg_set_error("level %d: large linear model is limited to data_dim <= %d", l, YG_BIG_MAX_DATA_DIM);
             return YG_ERR_UNSUPPORTED;
         }
-        if (!is_diagonal(L.noise_prec, L.data_dim) || !is_diagonal(L.prior_prec, d)) {
-            yg_set_error("level %d: large linear model needs diagonal noise and prior precision", l);
+        if (!is_diagonal(L.noise_prec, L.data_dim)) {
+            yg_set_error("level %d: large linear model needs diagonal measurement noise", l);
             return YG_ERR_UNSUPPORTED;
         }
         for (int r = 0; r < L.data_dim; r++)
@@ -161,14 +166,41 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
                 yg_set_error("level %d: negative noise precision", l);
                 return YG_ERR_INVALID;
             }
-        const size_t np = (size_t)(L.data_dim + 15) & ~size_t(15);
+        dense_prior[l] = !is_diagonal(L.prior_prec, d);
+        if (dense_prior[l]) {
+            // P = Lp Lp' (lower Cholesky); R = Lp' so that ||R x||^2 = x' P x.  DenseCovarianceMatrix priors
+            // (statistics/covariance.py:69-94) arrive here as their dense precision.
+            Rp[l].assign((size_t)d * d, 0.0);
+            std::vector<double> Lp((size_t)d * d, 0.0);
+            for (int j = 0; j < d; j++) {
+                double sdiag = L.prior_prec[(size_t)j * d + j];
+                for (int k = 0; k < j; k++) sdiag -= Lp[(size_t)j * d + k] * Lp[(size_t)j * d + k];
+                if (!(sdiag > 0.0)) {
+                    yg_set_error("level %d: the dense prior precision is not positive definite", l);
+                    return YG_ERR_INVALID;
+                }
+                Lp[(size_t)j * d + j] = sqrt(sdiag);
+                for (int i = j + 1; i < d; i++) {
+                    double v = 0.5 * (L.prior_prec[(size_t)i * d + j] + L.prior_prec[(size_t)j * d + i]);
+                    for (int k = 0; k < j; k++) v -= Lp[(size_t)i * d + k] * Lp[(size_t)j * d + k];
+                    Lp[(size_t)i * d + j] = v / Lp[(size_t)j * d + j];
+                }
+            }
+            for (int i = 0; i < d; i++)
+                for (int j = 0; j < d; j++) Rp[l][(size_t)i * d + j] = Lp[(size_t)j * d + i];
+        }
+        const size_t rows = (size_t)L.data_dim + (dense_prior[l] ? d : 0);
+        const size_t np = (rows + 15) & ~size_t(15);
         tail_len += np * ks + np + 2 * (size_t)kp;
     }
-    tail_len += 2 * (size_t)kp;
+    tail_len += 2 * (size_t)kp + (dense_L ? (size_t)kp * ks : 0);
     tail_len = (tail_len + 1) & ~size_t(1);
-    if (sizeof(double) * (tail_len + (size_t)16 * 8 * ks) > 226 * 1024) {      // blob + per-warp state tiles (16 warps x 8 chains)
-        yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
-        return YG_ERR_UNSUPPORTED;
+    {   // the blob and the tiles of at least four warps (state tile, noise tile, + a scratch tile for a dense factor)
+        const size_t per_warp = sizeof(double) * 8 * (size_t)ks * (dense_L ? 2 : 1) + sizeof(float) * 8 * (size_t)(kp + 4);
+        if (sizeof(double) * tail_len + 4 * per_warp > 226 * 1024) {
+            yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
+            return YG_ERR_UNSUPPORTED;
+        }
     }
     std::vector<char> blob(sizeof(DevBigHeader) + sizeof(double) * tail_len, 0);
     DevBigHeader *h = reinterpret_cast<DevBigHeader *>(blob.data());
@@ -177,6 +209,7 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     h->J = nl == 2 ? e->cfg.sub_chain_length : 1;
     h->tail_len = (int32_t)tail_len;
     h->proposal = pb->proposal;
+    h->dense_L = dense_L ? 1 : 0;
     if (pb->proposal == YG_PROPOSAL_PCN) {
         const double t = 2.0 * pb->pcn_step;                      // pcn.py:30
         h->pcn_a = sqrt(1.0 - t);
@@ -186,8 +219,9 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     for (int l = 0; l < nl; l++) {
         const yg_level &L = pb->level[l];
         BigLevel &B = h->lvl[l];
-        const int np = (L.data_dim + 15) & ~15;
-        B.n_data = L.n_data; B.data_dim = L.data_dim; B.np = np;
+        const int rows = L.data_dim + (dense_prior[l] ? d : 0);
+        const int np = (rows + 15) & ~15;
+        B.n_data = L.n_data; B.data_dim = L.data_dim; B.np = np; B.n_rows = rows;
         B.G_off = (int32_t)off;
         B.bd_off = (int32_t)(off + (size_t)np * ks);
         // sum_rows ||F - d_row||^2_P = sum_col n P_col (F_col - mean_col)^2 + sum_col P_col sum_rows (d - mean)^2;
@@ -208,13 +242,24 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
             tail[B.bd_off + r] = sw * (L.b[r] - mean);
             q_const += prec * scatter;
         }
+        if (dense_prior[l]) {                    // d more rows: R and -R m
+            for (int r = 0; r < d; r++) {
+                double rm = 0.0;
+                for (int k = 0; k < d; k++) {
+                    tail[off + (size_t)(L.data_dim + r) * ks + k] = Rp[l][(size_t)r * d + k];
+                    rm += Rp[l][(size_t)r * d + k] * L.prior_mean[k];
+                }
+                tail[B.bd_off + L.data_dim + r] = -rm;
+            }
+        }
         B.q_const = q_const;
         off += (size_t)np * ks + np;
         B.pmean_off = (int32_t)off;
         for (int k = 0; k < d; k++) tail[off + k] = L.prior_mean[k];
         off += kp;
         B.pprec_off = (int32_t)off;
-        for (int k = 0; k < d; k++) tail[off + k] = L.prior_prec[(size_t)k * d + k];
+        if (!dense_prior[l])
+            for (int k = 0; k < d; k++) tail[off + k] = L.prior_prec[(size_t)k * d + k];
         off += kp;
     }
     if (nl == 1) h->lvl[1] = h->lvl[0];
@@ -224,6 +269,11 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
     h->pcn_mean_off = (int32_t)off;
     if (pb->proposal == YG_PROPOSAL_PCN && pb->pcn_mean)
         for (int k = 0; k < d; k++) tail[off + k] = pb->pcn_mean[k];
+    off += kp;
+    h->Ld_off = (int32_t)off;
+    if (dense_L)
+        for (int r = 0; r < d; r++)
+            for (int k = 0; k <= r; k++) tail[off + (size_t)r * ks + k] = pb->prop_L[(size_t)r * d + k];
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     e->problem_set = false;
     if (e->d_problem) cudaFree(e->d_problem);
@@ -608,19 +658,27 @@ extern "C" int yg_set_proposal_factor(yg_ensemble *e, const double *L_host, void
     cudaStream_t st = (cudaStream_t)stream;
     YG_CUDA_CHECK(cudaSetDevice(e->cfg.device));
     if (e->big) {
-        if (!is_diagonal(L_host, d)) {
-            yg_set_error("large linear model: the proposal factor must be diagonal");
+        DevBigHeader *h = reinterpret_cast<DevBigHeader *>(e->h_problem.data());
+        if (!h->dense_L && !is_diagonal(L_host, d)) {
+            yg_set_error("large linear model: this handle was built for a diagonal proposal factor (its kernels and shared-"
+                         "memory plan differ for a dense one): pass a dense factor to yg_set_problem to switch");
             return YG_ERR_UNSUPPORTED;
         }
-        DevBigHeader *h = reinterpret_cast<DevBigHeader *>(e->h_problem.data());
         if (h->proposal != YG_PROPOSAL_MRW) {
             yg_set_error("the proposal factor of a pCN chain is the prior's (pcn.py:23-35) and cannot be replaced");
             return YG_ERR_UNSUPPORTED;
         }
         double *tail = reinterpret_cast<double *>(e->h_problem.data() + sizeof(DevBigHeader));
         for (int k = 0; k < d; k++) tail[h->propL_off + k] = L_host[(size_t)k * d + k];
-        char *dst = reinterpret_cast<char *>(e->d_problem) + sizeof(DevBigHeader) + sizeof(double) * h->propL_off;
-        YG_CUDA_CHECK(cudaMemcpyAsync(dst, tail + h->propL_off, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+        char *base = reinterpret_cast<char *>(e->d_problem) + sizeof(DevBigHeader);
+        YG_CUDA_CHECK(cudaMemcpyAsync(base + sizeof(double) * h->propL_off, tail + h->propL_off, sizeof(double) * d,
+                                      cudaMemcpyHostToDevice, st));
+        if (h->dense_L) {
+            for (int r = 0; r < d; r++)
+                for (int k = 0; k < d; k++) tail[h->Ld_off + (size_t)r * h->ks + k] = (k <= r) ? L_host[(size_t)r * d + k] : 0.0;
+            YG_CUDA_CHECK(cudaMemcpyAsync(base + sizeof(double) * h->Ld_off, tail + h->Ld_off,
+                                          sizeof(double) * (size_t)h->kp * h->ks, cudaMemcpyHostToDevice, st));
+        }
         return YG_OK;
     }
     DevProblemHeader *h = reinterpret_cast<DevProblemHeader *>(e->h_problem.data());

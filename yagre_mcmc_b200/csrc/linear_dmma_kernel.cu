@@ -272,11 +272,16 @@ constexpr int BIG_WARPS = 16;      // most warps per CTA (8 chains each, <= 128 
 __host__ __device__ constexpr int big_max_warps(int kq) { return kq == 16 ? YG_BIG_WARPS_KQ16 : BIG_WARPS; }
 // per-warp shared memory: the state tile [8][ks] doubles and the noise tile [8][4 KQ + 4] floats of the next proposal
 __host__ __device__ constexpr int big_zs(int kq) { return 4 * kq + 4; }
-inline size_t big_warp_bytes(int ks, int kq) { return sizeof(double) * 8 * (size_t)ks + sizeof(float) * 8 * (size_t)big_zs(kq); }
+// (+ a second [8][ks] tile when the proposal factor is dense: the transpose buffer of L z)
+inline size_t big_warp_bytes(int ks, int kq, bool dense_L)
+{
+    return sizeof(double) * 8 * (size_t)ks * (dense_L ? 2 : 1) + sizeof(float) * 8 * (size_t)big_zs(kq);
+}
 
-// FREE_NOISE = true: the production instance (Philox noise only).  The injected / recorded noise paths of the
-// parity tests live in the FREE_NOISE = false instance, which keeps the step loop of the production one small
-// enough for the instruction cache (stall reason no_instruction in profiles/r01_linear_dmma.md).
+// FREE_NOISE = true: the production instance (Philox noise, diagonal proposal factor).  The injected / recorded noise
+// paths of the parity tests and the DENSE proposal factor (p = s + L z with L z as a second small GEMM) live in the
+// FREE_NOISE = false instance, which keeps the step loop of the production one small enough for the instruction cache
+// (stall reason no_instruction in profiles/r01_linear_dmma.md).
 template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
 __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
                                                                           long long *tile_done)
@@ -308,8 +313,11 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
     constexpr int ZS = big_zs(KQ);
     const int n_warps = blockDim.x >> 5;
-    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks + 4 * ZS);       // 8 ZS floats = 4 ZS doubles
-    float *zb = reinterpret_cast<float *>(ths + 8 * ks);
+    const bool dense_L = !FREE_NOISE && H.dense_L;
+    const double *Ld = smem + H.Ld_off;            // [kp][ks] lower-triangular proposal factor (dense_L only)
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks * (dense_L ? 2 : 1) + 4 * ZS);   // 8 ZS floats = 4 ZS doubles
+    double *scr = ths + 8 * ks;                    // [8][ks] transpose buffer of L z (dense_L only)
+    float *zb = reinterpret_cast<float *>(ths + 8 * ks * (dense_L ? 2 : 1));
 #define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
@@ -405,22 +413,44 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         auto propose = [&](auto &&src, int64_t n, int j, double (&p)[KQ]) {
             bool same = true;
             __syncwarp();                                  // the noise tile was written by other lanes
+            double zv[KQ];
 #pragma unroll
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
-                double zv = 0.0;
+                zv[i] = 0.0;
                 if (noise_mode == YG_NOISE_INJECT) {
-                    if (k < d) zv = a.z[((n * J + j) * d + k) * N + gg];
+                    if (k < d) zv[i] = a.z[((n * J + j) * d + k) * N + gg];
                 } else if (k < d) {
-                    zv = (double)zb[g * ZS + k];
-                    if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv;
+                    zv[i] = (double)zb[g * ZS + k];
+                    if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[i];
                 }
+            }
+            if (dense_L) {
+                // L z of the 8 chains as a GEMM: L is the A operand (16 rows x 4 columns per mma), z -- already in the
+                // B-fragment layout -- the other one; only the k-steps of the lower triangle are issued.  The accumulators
+                // hold (L z)[row][chain]; the scratch tile transposes them back to "lane (g, t) holds chain g, row 4i + t".
+                for (int nb = 0; nb < H.kp; nb += 16) {
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                    const double *Lb = Ld + (size_t)(nb + g) * ks + t;
+#pragma unroll
+                    for (int i = 0; i < KQ; i++)
+                        if (4 * i <= nb + 15) dmma_m16n8k4(c0, c1, c2, c3, Lb[4 * i], Lb[(size_t)8 * ks + 4 * i], zv[i]);
+                    scr[(2 * t) * ks + nb + g] = c0;
+                    scr[(2 * t + 1) * ks + nb + g] = c1;
+                    scr[(2 * t) * ks + nb + 8 + g] = c2;
+                    scr[(2 * t + 1) * ks + nb + 8 + g] = c3;
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
                 const double sv = src(i);
-                const double lz = __dmul_rn(propL[k], zv);
+                const double lz = dense_L ? scr[g * ks + k] : __dmul_rn(propL[k], zv[i]);
                 p[i] = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[k], lz))) : __dadd_rn(sv, lz);
                 same = same && (p[i] == sv);
             }
-            __syncwarp();                                  // every lane has read its columns: the tile may be refilled
+            __syncwarp();                                  // every lane has read its columns: the tiles may be refilled
             // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
             const unsigned m = __ballot_sync(0xffffffffu, same);
             return ((m >> (4 * g)) & 0xFu) == 0xFu;
@@ -609,7 +639,7 @@ __global__ void big_logpost_kernel(const DevBigHeader *gh, int lvl, const double
     const double *pm = tail + L.pmean_off, *pw = tail + L.pprec_off;
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int col = 0; col < L.data_dim; col++) {
+        for (int col = 0; col < L.n_rows; col++) {
             double f = 0.0;
             for (int k = 0; k < H.dim; k++) f = fma(G[(size_t)col * H.ks + k], theta[(int64_t)k * n + c], f);
             const double e = f + bd[col];
@@ -648,7 +678,8 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
     // warps per CTA: as many as the shared memory left by the problem blob holds (13 at d = 64 x 256, else 16)
-    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1)), per_warp = big_warp_bytes(hh->ks, KQ);
+    const bool dense_L = hh->dense_L != 0;
+    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1)), per_warp = big_warp_bytes(hh->ks, KQ, dense_L);
     const size_t budget = 227 * 1024;
     int warps = blob < budget ? (int)std::min<size_t>(big_max_warps(KQ), (budget - blob) / per_warp) : 0;
     if (warps < 4) {
@@ -656,7 +687,7 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
         return YG_ERR_UNSUPPORTED;
     }
     const size_t smem = blob + (size_t)warps * per_warp;
-    const bool free_noise = a.noise_mode == YG_NOISE_PHILOX;
+    const bool free_noise = a.noise_mode == YG_NOISE_PHILOX && !dense_L;      // the general instance also knows dense factors
     auto kern = e->cfg.n_levels == 2
                     ? (free_noise ? linear_dmma_mh_kernel<KQ, true, true> : linear_dmma_mh_kernel<KQ, true, false>)
                     : (free_noise ? linear_dmma_mh_kernel<KQ, false, true> : linear_dmma_mh_kernel<KQ, false, false>);
