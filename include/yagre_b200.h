@@ -71,8 +71,9 @@ extern "C" {
 #define YG_MAX_LEVELS 3         /* densities per problem: up to two surrogates + the target */
 #define YG_MAX_DIM 8           /* parameter dimension of the one-chain-per-thread kernels */
 #define YG_MAX_DATA_DIM 8
-/* YG_MODEL_LINEAR beyond those sizes runs on the FP64 tensor path (DMMA GEMM, linear_dmma_kernel.cu):
- * diagonal noise / prior precision and diagonal proposal factor, n_data <= 8, no adaptive Metropolis;
+/* YG_MODEL_LINEAR beyond those sizes runs on the FP64 tensor path (DMMA GEMM, linear_dmma_kernel.cu): MRW, pCN and
+ * two-level delayed acceptance; diagonal measurement noise; diagonal or dense prior precision and proposal factor;
+ * any number of data rows; no adaptive Metropolis / adaptive error model / third level / tempering;
  * Welford M2 is then diagonal only ([d, n_chains] instead of [d, d, n_chains]). */
 #define YG_BIG_MAX_DIM 64
 #define YG_BIG_MAX_DATA_DIM 256
