@@ -686,14 +686,18 @@ def measure_other_configs(device, fp64_peak, main_value, hbm_peak_gbs):
     for (d_, dd_, two, J_, key) in ((64, 256, False, 1, "linear_d64_x256_65536"), (32, 96, True, 3, "linear_d32_x96_two_level_65536")):
         meta, arrays = bp.big_linear_problem(d_, dd_, 1, two_level=two, J=J_)
         mean, _ = bp.linear_gaussian_posterior(arrays, meta["levels"] - 1)
-        ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5)
-        ens.set_state(np.tile(mean, (65536, 1)))
-        ms, c = timed(ens, 50)
-        fl = bp.big_linear_flops_per_eval(d_, dd_) * (c["coarse_evals"] + c["fine_evals"])
-        out[key] = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
-                    "fp64_tflops": fl / ms * 1e-9, "dmma_peak_tflops": tpeak, "frac_of_dmma_peak": fl / ms * 1e-9 / tpeak,
-                    "kernel": "linear_dmma_mh_kernel"}
-        ens.close()
+        for welford in (True, False):
+            ens = ChainEnsemble(LoweredProblem(meta, arrays), 65536, device=device, seed=5, welford=welford)
+            ens.set_state(np.tile(mean, (65536, 1)))
+            ms, c = timed(ens, 50)
+            fl = bp.big_linear_flops_per_eval(d_, dd_) * (c["coarse_evals"] + c["fine_evals"])
+            e = {"chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+                 "fp64_tflops": fl / ms * 1e-9, "dmma_peak_tflops": tpeak, "frac_of_dmma_peak": fl / ms * 1e-9 / tpeak,
+                 "kernel": "linear_dmma_mh_kernel",
+                 "diagnostics": "FullDiagnostics (Welford moments of every chain maintained in L2)" if welford else
+                                "AcceptanceRateDiagnostics (the default of the reference's builders, chain/builder.py:14-16)"}
+            out[key if welford else key + "_acceptance_diagnostics"] = e
+            ens.close()
     return out
 
 

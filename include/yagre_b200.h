@@ -171,7 +171,12 @@ typedef struct yg_config {
     int32_t aem;                /* 0 / 1 */
     int32_t aem_min_data;       /* minDataSize >= 2 */
     int32_t aem_heuristic;      /* useNoiseHeuristic: scaling = min(2 max(var) / max(min(var), 1e-6), 100) */
-    int32_t reserved[2];
+    /* 0 (default) = FullDiagnostics: the Welford moments w_mean / w_m2 of the pre-transition states are maintained
+     * (chain/diagnostics.py:67-107); 1 = AcceptanceRateDiagnostics only -- the default diagnostics of the reference's
+     * builders (chain/builder.py:14-16) -- : they stay zero.  Honoured by the tensor-path kernel, where the moments
+     * live in L2 (d x 2 doubles per chain); the other kernels keep them in registers / shared memory for free. */
+    int32_t acceptance_only;
+    int32_t reserved[1];
 } yg_config;
 
 typedef struct yg_noise {

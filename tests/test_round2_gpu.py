@@ -452,3 +452,26 @@ def test_dmma_path_dense_covariances_posterior_moments():
         diag.set_proposal_factor(arrays["prop_L"])
     ens.set_proposal_factor(0.5 * arrays["prop_L"])                      # a dense handle takes another dense factor
     ens.run(5, samples=False)
+
+
+def test_dmma_acceptance_only_diagnostics_skips_the_moments_and_nothing_else():
+    """yg_config.acceptance_only (the reference builders' default AcceptanceRateDiagnostics, chain/builder.py:14-16):
+    the tensor-path kernel does not maintain the Welford moments; trajectories, decisions and counters are unchanged."""
+    meta, arrays = bp.big_linear_problem(32, 96, 2, two_level=True, J=3)
+    nc, ns = 3000, 25
+    th0 = 0.01 * np.random.default_rng(5).standard_normal((nc, 32))
+    res = []
+    for welford in (True, False):
+        ens = _ens(meta, arrays, nc, seed=9, welford=welford)
+        ens.set_state(th0)
+        out = ens.run(ns, samples=True, accepted=True, logpost=True)
+        res.append((out, ens.state(), ens.counters()))
+    for k in ("samples", "accepted", "logpost"):
+        assert torch.equal(res[0][0][k], res[1][0][k]), k
+    assert res[0][2] == res[1][2]
+    assert float(res[1][1]["w_mean"].abs().sum()) == 0.0 and float(res[1][1]["w_m2"].abs().sum()) == 0.0
+    assert float(res[0][1]["w_m2"].abs().sum()) > 0.0 and res[1][1]["welford_n"] == ns
+    x = res[0][0]["samples"].cpu().numpy()                        # Welford of the PRE-transition states: th0, x[0..ns-2]
+    pre = np.concatenate([th0.T[None], x[:-1]], axis=0)
+    np.testing.assert_allclose(res[0][1]["w_mean"].cpu().numpy(), pre.mean(0), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(res[0][1]["w_m2"].cpu().numpy(), ((pre - pre.mean(0)) ** 2).sum(0), rtol=1e-9, atol=1e-14)

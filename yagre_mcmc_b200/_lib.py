@@ -55,7 +55,7 @@ class YgConfig(C.Structure):
                 ("am_eps", C.c_double), ("am_scale", C.c_double),
                 ("blocks_per_sm", C.c_int32), ("threads_per_block", C.c_int32),
                 ("rk4_segment", C.c_int32), ("aem", C.c_int32), ("aem_min_data", C.c_int32),
-                ("aem_heuristic", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("aem_heuristic", C.c_int32), ("acceptance_only", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class YgNoise(C.Structure):

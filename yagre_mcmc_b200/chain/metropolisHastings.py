@@ -49,10 +49,19 @@ class MetropolisHastings:
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         self._ensemble = ChainEnsemble(lowered, self._nLocal, device=device, seed=self._seed,
-                                       chain_offset=self._offset, adaptive=adaptive, aem=aem, **(launch or {}))
+                                       chain_offset=self._offset, adaptive=adaptive, aem=aem,
+                                       welford=self._wants_moments(diagnostics), **(launch or {}))
         self._last = None
         self._ran = False               # a run() has set the device state at least once
         self._diagnosticsCleared = True  # clear() was called since the last run(): restart the device accumulators
+
+    @staticmethod
+    def _wants_moments(diagnostics):
+        """FullDiagnostics keeps Welford moments (chain/diagnostics.py:67-107); the builders' default
+        AcceptanceRateDiagnostics does not (chain/builder.py:14-16).  Only the tensor-path kernel saves work by it:
+        the other kernels keep the moments for free, and pooled() / pool_proposal_covariance() rely on them there."""
+        from .diagnostics import FullDiagnostics
+        return isinstance(diagnostics, FullDiagnostics)
 
     # ---- reference surface ------------------------------------------------------------------
     @property

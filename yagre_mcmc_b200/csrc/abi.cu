@@ -84,6 +84,7 @@ RunArgs make_args(yg_ensemble *e)
     a.aem = e->cfg.aem;
     a.aem_min_data = e->cfg.aem_min_data;
     a.aem_heuristic = e->cfg.aem_heuristic;
+    a.welford = e->cfg.acceptance_only ? 0 : 1;
     a.aem_n = e->aem_n;
     a.aem_mean = e->aem_mean;
     a.aem_m2 = e->aem_m2;

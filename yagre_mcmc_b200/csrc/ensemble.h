@@ -26,7 +26,8 @@ struct RunArgs {
     int64_t am_idle, am_collect;
     double am_eps, am_scale;
     // adaptive error model (generic kernel, two level, linear model)
-    int32_t aem, aem_min_data, aem_heuristic, _pad_aem;
+    int32_t aem, aem_min_data, aem_heuristic;
+    int32_t welford;                // 0: acceptance-only diagnostics, the Welford moments are not maintained (tensor path)
     unsigned long long *aem_n;      // [n]
     double *aem_mean, *aem_m2;      // [data_dim, n]
     double *aem_cache;              // [3 (d + 1) + 1, n]

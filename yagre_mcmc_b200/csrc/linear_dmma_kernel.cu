@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         // columns are issued before any store (a store may alias the next load for the compiler).
         double run = 0.0, wn = (double)(a.welford_n0 + s0);
         auto welford_flush = [&](const bool f) {
-            const bool fl = f && live && run != 0.0;
+            const bool fl = f && live && run != 0.0 && a.welford;
             if (!__any_sync(0xffffffffu, fl)) return;
             const double n1 = wn + run, c1 = run / n1, c2 = wn * c1;
             constexpr int B = KQ < 8 ? KQ : 8;

@@ -87,7 +87,7 @@ class ChainEnsemble:
     """n_chains independent chains of one problem on one device."""
 
     def __init__(self, problem, n_chains, device=0, seed=0, chain_offset=0,
-                 adaptive=None, blocks_per_sm=0, threads_per_block=0, rk4_segment=0, aem=None):
+                 adaptive=None, blocks_per_sm=0, threads_per_block=0, rk4_segment=0, aem=None, welford=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.BackendUnavailable("no CUDA device visible: the batched-chain backend has no CPU fallback")
@@ -111,6 +111,9 @@ class ChainEnsemble:
         cfg.blocks_per_sm = int(blocks_per_sm)
         cfg.threads_per_block = int(threads_per_block)
         cfg.rk4_segment = int(rk4_segment)
+        # welford=False: AcceptanceRateDiagnostics only (the reference builders' default, chain/builder.py:14-16);
+        # honoured by the tensor-path kernel, whose Welford moments live in L2
+        cfg.acceptance_only = 0 if welford else 1
         self.aem = None
         if aem:             # adaptive error model: dict(min_data=..., heuristic=...)
             cfg.aem = 1
