@@ -470,6 +470,28 @@ def run_gpu_arm(args):
         ess["adaptive"] = ess_of(ens_am, burn_ms, "per-chain adaptive Metropolis (idle 50, collection 300, refresh 10 coarse "
                                                   "proposals) after %d burn-in transitions" % args.pool_burnin)
         ens_am.close()
+        # tuned arm (profiles/r02_ess_sweep.txt): the sub-chain length is a user parameter like the proposal; J = 8
+        # coarse steps with the pooled proposal covariance make almost every fine step an independent draw
+        # (IAT_max -> 1) -- fewer chain-steps/s, more than twice the ESS/s of the example's J = 3 / 0.1 I
+        meta_t, arrays_t = bp.lv_problem(True, J=args.tuned_j)
+        ens_t = ChainEnsemble(LoweredProblem(meta_t, arrays_t), nc, device=local, seed=args.seed + 2, chain_offset=offset)
+        ens_t.set_state(th0)
+        barrier()
+        _, burn_ms = timed_run(ens_t, args.pool_burnin, samples=False)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pooled_t = pooled_proposal_covariance(ens_t)
+        last = ens_t.state()["theta"].t().contiguous()
+        ens_t.set_state(last)
+        p1.record()
+        torch.cuda.synchronize(dev)
+        ess["tuned"] = ess_of(ens_t, burn_ms + p0.elapsed_time(p1),
+                              "sub-chain length J = %d (the example uses 3) + pooled proposal covariance chol(2.4^2/d Sigma_pooled) "
+                              "after %d burn-in transitions" % (args.tuned_j, args.pool_burnin))
+        ess["tuned"]["sub_chain_length"] = args.tuned_j
+        ess["tuned"]["prop_L"] = [[float(x) for x in row] for row in pooled_t["prop_L"]]
+        ess["tuned"]["over_example"] = ess["tuned"]["ess_per_s"] / ess["ess_per_s"]
+        ens_t.close()
         del ess_buf
 
     # ---- the other BASELINE.json configs, briefly (rank 0, N = 1): parity-tested elsewhere, timed here ----
@@ -732,6 +754,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --chains per GPU; strong: 524,288 chains in total (BASELINE.json configs[4])")
     ap.add_argument("--pool-burnin", type=int, default=500, help="burn-in transitions before the proposal covariance is pooled")
+    ap.add_argument("--tuned-j", type=int, default=8, help="sub-chain length of the tuned ESS arm (profiles/r02_ess_sweep.txt)")
     ap.add_argument("--burnin", type=int, default=100)
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--ess-steps", type=int, default=5000)

@@ -53,7 +53,8 @@ def test_b200_arm_line():
     assert e["h2d_bytes_per_step"] == 8192 * 2 * 8 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= 1.05 * d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["ess_per_s"] > 0
     assert d["cpu_cores"] == d["cpu_baseline"]["cores"] and d["scaling"] == "weak"
-    for arm in ("pooled", "adaptive"):
+    assert d["ess"]["tuned"]["sub_chain_length"] == 8 and d["ess"]["tuned"]["over_example"] > 0.0   # > 2 at the real sizes (short test chains pay the burn-in)
+    for arm in ("pooled", "adaptive", "tuned"):
         assert d["ess"][arm]["ess_per_s"] > 0 and d["ess"][arm]["degenerate_chains"] == 0
         assert all(abs(x - 1.0) < 0.05 for x in d["ess"][arm]["diagnostics"]["split_rhat"])
     dg = d["ess"]["diagnostics"]
