@@ -246,8 +246,9 @@ int yg_get_state(yg_ensemble *e, const yg_state *dst, void *stream);
 int yg_load_state(yg_ensemble *e, const yg_state *src, int64_t step_index, int64_t welford_n, int64_t am_steps,
                   void *stream);
 
-/* out_host[8] = {step index, transitions done (all chains), accepted, level-0 forward evals,
- * target-level forward evals, welford n, am_steps, level-1 forward evals of a three-level hierarchy}.
+/* out_host[9] = {step index, transitions done (all chains), accepted, level-0 forward evals,
+ * target-level forward evals, welford n, am_steps, level-1 forward evals of a three-level hierarchy,
+ * accepted coarse sub-steps (the acceptance the reference's surrogate diagnostics record, mlda.py:58-62)}.
  * Synchronises `stream`. */
 int yg_get_counters(yg_ensemble *e, int64_t *out_host, void *stream);
 

@@ -463,3 +463,25 @@ def test_verbose_run_and_clear(capsys):
     assert mc.chain.length == 0 and mc.diagnostics.global_acceptance_rate() == 0.0
     mc.run(1, ParameterVector(np.zeros(2)), verbose=False)      # chainLength 1 = just the initial state
     assert np.asarray(mc.chain.trajectory).shape == (1, 8, 2)
+
+
+def test_surrogate_diagnostics_record_the_coarse_acceptance():
+    """user-supplied surrogateDiagnostics are fed (reference: the MRW of the surrogate hierarchy processes
+    every coarse step, chain/method/mlda.py:58-62).  The kernels count accepted coarse sub-steps of the ensemble."""
+    tgtMean, tgtCov, tgt, sur = _mlda_targets(np.array([0.1, -0.2]), 1.5 * np.array([[2.5, -0.3], [-0.3, 0.9]]))
+    b = MLDABuilder()
+    b.explicitTarget = tgt
+    b.surrogateTargets = [sur]
+    b.baseProposalCovariance = IIDCovarianceMatrix(2, 1.0)
+    b.subChainLengths = [10]
+    b.surrogateDiagnostics = [AcceptanceRateDiagnostics()]
+    b.nChains, b.seed = 256, 1
+    mc = b.build_method()
+    mc.run(500, ParameterVector(np.array([1.0, 1.5])), verbose=False)
+    coarse = b.surrogateDiagnostics[0].global_acceptance_rate()
+    c = mc.ensemble.counters()
+    assert c["coarse_accepted"] > 0 and coarse == c["coarse_accepted"] / (c["transitions"] * 10)
+    assert 0.3 < coarse < 0.8 and coarse != mc.diagnostics.global_acceptance_rate()
+    mc.clear()
+    mc.run(100, ParameterVector(np.array([1.0, 1.5])), verbose=False)
+    assert mc.ensemble.counters()["transitions"] == 256 * 99          # clear() restarted the device counters too

@@ -16,6 +16,9 @@ class DummyDiagnostics(ChainDiagnostics):
     def process_ensemble(self, stats):
         return
 
+    def process_totals(self, n_accept_total, n_decisions_total):
+        return
+
     def print_diagnostics(self, logger):
         return
 
@@ -50,12 +53,24 @@ class AcceptanceRateDiagnostics(ChainDiagnostics):
         elif self._n_transitions:
             self._rolling = self.global_acceptance_rate()
 
+    def process_totals(self, n_accept_total, n_decisions_total):
+        """Ensemble totals only (the coarse sub-chains of delayed acceptance live inside the step kernels, which
+        count their accepted sub-steps but keep no per-chain record): feeds global_acceptance_rate()."""
+        prev = self._totals
+        self._totals = (int(n_accept_total), int(n_decisions_total))
+        if prev is not None and self._totals[1] > prev[1]:
+            self._rolling = (self._totals[0] - prev[0]) / float(self._totals[1] - prev[1])
+        elif self._totals[1]:
+            self._rolling = self._totals[0] / float(self._totals[1])
+
     def acceptance_rates(self):
         if self._n_accept is None or not self._n_transitions:
             return None
         return self._n_accept / float(self._n_transitions)
 
     def global_acceptance_rate(self):
+        if self._totals is not None:
+            return self._totals[0] / float(self._totals[1]) if self._totals[1] else 0.0
         if self._n_accept is None or not self._n_transitions:
             return 0.0
         return float(self._n_accept.sum()) / (self._n_transitions * self._n_accept.size)
@@ -75,6 +90,7 @@ class AcceptanceRateDiagnostics(ChainDiagnostics):
         self._n_accept = None
         self._n_transitions = 0
         self._rolling = None
+        self._totals = None
 
 
 class FullDiagnostics(ChainDiagnostics):
@@ -98,6 +114,9 @@ class FullDiagnostics(ChainDiagnostics):
         self._diagnostics.process_ensemble(stats)
         self._squeeze = stats.get('squeeze', False)
         self._accumulator.load(stats['welford_n'], stats['w_mean'], stats['w_m2_diag'])
+
+    def process_totals(self, n_accept_total, n_decisions_total):
+        self._diagnostics.process_totals(n_accept_total, n_decisions_total)
 
     def global_acceptance_rate(self):
         return self._diagnostics.global_acceptance_rate()

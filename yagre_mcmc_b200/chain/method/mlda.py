@@ -73,10 +73,7 @@ class MLDA(MetropolisHastings):
                          device=device, thin=thin, storeTrajectory=storeTrajectory, launch=launch, aem=aem,
                          adaptive=adaptive)
         self._surrogateDiagnostics = surrogateDiagnosticsList
-        if any(not isinstance(dg, DummyDiagnostics) for dg in (surrogateDiagnosticsList or [])):
-            import warnings
-            warnings.warn("surrogate diagnostics are not fed by the device: coarse sub-chains live inside the "
-                          "step kernels; evaluation_counts() reports the coarse forward evaluations", stacklevel=3)
+        self._J = J
         for lvl, t in enumerate(levels):
             if isinstance(t, UnnormalisedPosterior):
                 t.bind(self._ensemble, lvl)
@@ -87,6 +84,17 @@ class MLDA(MetropolisHastings):
 
     def surrogate(self, sIdx):
         return self._proposalMethod.surrogate(sIdx)
+
+    def _update_diagnostics(self):
+        """+ the base surrogate's diagnostics (reference: the MRW of SurrogateHierarchy level 0 records every coarse
+        step, mlda.py:58-62): the kernels count the accepted coarse sub-steps of the ensemble; per-chain coarse rates
+        are not kept.  With two surrogates the second surrogate's diagnostics see nothing, as in the reference (its
+        _accept_reject is never called, mlda.py:112-117)."""
+        super()._update_diagnostics()
+        dg = (self._surrogateDiagnostics or [None])[0]
+        if dg is not None and hasattr(dg, "process_totals"):
+            c = self._ensemble.counters()
+            dg.process_totals(c["coarse_accepted"], c["transitions"] * self._J)
 
     def evaluation_counts(self):
         """Forward evaluations actually performed (coarse, fine) -- skipped ones do not count."""

@@ -845,6 +845,7 @@ extern "C" int yg_get_counters(yg_ensemble *e, int64_t *out_host, void *stream)
     out_host[5] = e->welford_n;
     out_host[6] = e->am_steps;
     out_host[7] = (int64_t)c[4];
+    out_host[8] = (int64_t)c[5];
     return YG_OK;
 }
 

@@ -44,6 +44,7 @@ struct RunArgs {
     double lv_h[2];
     LvStepConsts lv_k[2];
     // [0] transitions [1] accepted [2] level-0 evals [3] target-level evals [4] level-1 evals of three levels
+    // [5] accepted coarse sub-steps (what the reference's surrogate diagnostics count, chain/method/mlda.py:58-62)
     unsigned long long *counters;
 };
 

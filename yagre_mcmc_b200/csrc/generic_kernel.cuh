@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
     const int64_t N = a.n_chains;
     const bool isclose_eq = pb->eq_mode == YG_EQ_ISCLOSE;
     const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
-    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_ev2 = 0ull, cnt_tr = 0ull;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_ev2 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
 
     const int ws_lane = threadIdx.x & 31;
     const int ws_per_step = TWO_LEVEL ? J + 1 : 1;       // ring entries per transition
@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
 #pragma unroll
                         for (int i = 0; i < D; i++) s[i] = p[i];
                         lps = lpp;
+                        cnt_cacc++;
                     }
                 }
                 if (WS) ws_fetch();
@@ -512,9 +513,9 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
         a.n_accept[g] = nacc;
     }
     // ---- counters: warp-shuffle reduction, one atomic per warp ------------------------------
-    unsigned long long v[5] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_ev2};
+    unsigned long long v[6] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_ev2, cnt_cacc};
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 6; k++) {
         if (WS) {                                   // exited lanes (chains beyond N, producers) cannot shuffle
             if (v[k]) atomicAdd(&a.counters[k], v[k]);
             continue;
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
     const int dd = Lc.data_dim, nD = Lc.n_data;
     const double *data = dev_tail(pb) + Lc.data_off;
     const int64_t N = a.n_chains;
-    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
 
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < N; g += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t gid = (uint64_t)(a.chain_offset + g);
@@ -796,6 +797,7 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
                 if (accept_rule(lpp - lps, u)) {
 #pragma unroll
                     for (int i = 0; i < D; i++) s[i] = p[i];
+                    cnt_cacc++;
                 }
             }
             if (!equal(s, th)) {
@@ -884,12 +886,12 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
             }
         }
     }
-    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+    unsigned long long v[5] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_cacc};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 5; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&a.counters[k == 4 ? 5 : k], v[k]);
     }
 }
 

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     float *zb = reinterpret_cast<float *>(ths + 8 * ks * (dense_L ? 2 : 1));
 #define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
-    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull;
+    unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
 
     // ---- one piece of work: transitions [s0, s1) of the 8 chains of `tile` -------------------------------------
     auto run_piece = [&](const int64_t tile, const int64_t s0, const int64_t s1) {
@@ -517,6 +517,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
 #pragma unroll
                         for (int i = 0; i < KQ; i++) s[i] = p[i];
                         lps = lpp;
+                        if (t == 0 && live) cnt_cacc++;
                     }
                 }
                 // the sub-chain's end point is the proposal; no fine evaluation for a chain that did
@@ -592,6 +593,9 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     };
 
     // ---- balanced schedule: this warp's contiguous range of the (tile-major, step-minor) work list ------------------
+    // A warp only ever waits for the warp with the next lower global index (same CTA or the CTA with the next lower
+    // blockIdx), which never waits for a higher one: with CTAs dispatched in index order nothing can wait for a CTA that
+    // is not resident yet, even if the grid shares the GPU with other work.
     const int64_t n_tiles = (N + 7) / 8, S = a.n_steps;
     const int64_t gw = (int64_t)blockIdx.x * n_warps + warp, GW = (int64_t)gridDim.x * n_warps;
     // ranges in units of transitions: [lo, hi); n_tiles * S < 2^63 / GW for every admissible size
@@ -619,12 +623,12 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     }
 #undef TH
     // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
-    unsigned long long v[4] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1};
+    unsigned long long v[5] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_cacc};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 5; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        if (lane == 0 && v[k]) atomicAdd(&a.counters[k], v[k]);
+        if (lane == 0 && v[k]) atomicAdd(&a.counters[k == 4 ? 5 : k], v[k]);
     }
 }
 

@@ -136,11 +136,11 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     off = (off + 15) & ~size_t(15);      // the int arrays above leave 4-byte alignment when n_data * cmax is odd
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + off);
     int *nact = reinterpret_cast<int *>(mbar + 1);                         // [2]
-    unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [4]
-    int *qhead = reinterpret_cast<int *>(mbar + 6);                        // work-queue head of the current phase
+    unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [5]
+    int *qhead = reinterpret_cast<int *>(mbar + 7);                        // work-queue head of the current phase
 
     tma_stage_blob(pb, a.problem, (uint32_t)((a.problem_bytes + 15u) & ~15u), mbar);
-    if (tid < 4) blk_cnt[tid] = 0ull;
+    if (tid < 5) blk_cnt[tid] = 0ull;
     if (tid < 2) nact[tid] = 0;
 
     const double *tail = dev_tail(pb);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
             nacc[c] = a.n_accept[g];
             if (a.n_steps > 0) draw_z(c, g, 0, 0);
         }
-        unsigned long long my_acc = 0ull;
+        unsigned long long my_acc = 0ull, my_cacc = 0ull;      // accepted transitions / accepted coarse sub-steps
 
         int64_t thin_left = a.thin, thin_out = -1;
         for (int64_t n = 0; n < a.n_steps; n++) {
@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                             const double lpp = log_post_from_q(0, c, p0, p1);
                             if (accept_rule(lpp - lps, nz[2 * cmax + c])) {      // u_c(n, j-1)
                                 s0 = p0; s1 = p1; lps = lpp;
+                                my_cacc += 1ull;
                             }
                         }
                     }
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
             a.n_accept[g] = nacc[c];
         }
         if (my_acc) atomicAdd(&blk_cnt[1], my_acc);
+        if (my_cacc) atomicAdd(&blk_cnt[4], my_cacc);
         if (tid == 0) blk_cnt[0] += (unsigned long long)C * (unsigned long long)a.n_steps;
     }
     __syncthreads();
@@ -527,6 +529,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     }
 #endif
     if (tid < 4 && blk_cnt[tid]) atomicAdd(&a.counters[tid], blk_cnt[tid]);
+    if (tid == 4 && blk_cnt[4]) atomicAdd(&a.counters[5], blk_cnt[4]);       // [4] is the middle level of three-level problems
 #undef CH
 }
 
@@ -541,7 +544,7 @@ size_t lv_smem_bytes(const yg_ensemble *e, int cmax, int nd_max)
     off += sizeof(int) * (size_t)nd_max * cmax;           // segdone
     off += (cmax + 15) & ~15;
     off = (off + 15) & ~size_t(15);
-    off += 8 + 8 + 32 + 8;
+    off += 8 + 8 + 40 + 8;
     return (off + 15) & ~size_t(15);
 }
 

@@ -307,11 +307,11 @@ class ChainEnsemble:
         return self
 
     def counters(self):
-        buf = (C.c_int64 * 8)()
+        buf = (C.c_int64 * 9)()
         with torch.cuda.device(self.device):
             check(self.lib.yg_get_counters(self._h, buf, self._stream()))
         keys = ('step_index', 'transitions', 'accepted', 'coarse_evals', 'fine_evals', 'welford_n', 'am_steps',
-                'mid_evals')
+                'mid_evals', 'coarse_accepted')
         c = dict(zip(keys, [int(x) for x in buf]))
         if self.levels == 1:        # single level: level 0 IS the target
             c['fine_evals'], c['coarse_evals'] = c['coarse_evals'], 0
