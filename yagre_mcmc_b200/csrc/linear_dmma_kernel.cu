@@ -273,9 +273,9 @@ __host__ __device__ constexpr int big_max_warps(int kq) { return kq == 16 ? YG_B
 // per-warp shared memory: the state tile [8][ks] doubles and the noise tile [8][4 KQ + 4] floats of the next proposal
 __host__ __device__ constexpr int big_zs(int kq) { return 4 * kq + 4; }
 // (+ a second [8][ks] tile when the proposal factor is dense: the transpose buffer of L z)
-inline size_t big_warp_bytes(int ks, int kq, bool dense_L)
+inline size_t big_warp_bytes(int ks, int kq, bool dense_L, bool wsm)
 {
-    return sizeof(double) * 8 * (size_t)ks * (dense_L ? 2 : 1) + sizeof(float) * 8 * (size_t)big_zs(kq);
+    return sizeof(double) * 8 * (size_t)ks * (1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0)) + sizeof(float) * 8 * (size_t)big_zs(kq);
 }
 
 // FREE_NOISE = true: the production instance (Philox noise, diagonal proposal factor).  The injected / recorded noise
@@ -284,7 +284,7 @@ inline size_t big_warp_bytes(int ks, int kq, bool dense_L)
 // (stall reason no_instruction in profiles/r01_linear_dmma.md).
 template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
 __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
-                                                                          long long *tile_done)
+                                                                          long long *tile_done, const int wsm)
 {
     const int noise_mode = FREE_NOISE ? (int)YG_NOISE_PHILOX : a.noise_mode;
     extern __shared__ __align__(16) double smem[];
@@ -315,9 +315,15 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     const int n_warps = blockDim.x >> 5;
     const bool dense_L = !FREE_NOISE && H.dense_L;
     const double *Ld = smem + H.Ld_off;            // [kp][ks] lower-triangular proposal factor (dense_L only)
-    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks * (dense_L ? 2 : 1) + 4 * ZS);   // 8 ZS floats = 4 ZS doubles
-    double *scr = ths + 8 * ks;                    // [8][ks] transpose buffer of L z (dense_L only)
-    float *zb = reinterpret_cast<float *>(ths + 8 * ks * (dense_L ? 2 : 1));
+    // per-warp tiles: state [8][ks]; (dense factor only) the transpose buffer of L z [8][ks]; (wsm: when shared memory
+    // allows) the Welford mean and second moment of the tile, 2 x [8][ks]; the noise tile [8][ZS] floats
+    const int n_dtiles = 1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0);
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks * n_dtiles + 4 * ZS);   // 8 ZS floats = 4 ZS doubles
+    double *scr = ths + 8 * ks;                    // (dense_L only)
+    double *wmt = ths + 8 * ks * (dense_L ? 2 : 1), *wvt = wmt + 8 * ks;      // (wsm only)
+    float *zb = reinterpret_cast<float *>(ths + 8 * ks * n_dtiles);
+#define WM(i) wmt[g * ks + 4 * (i) + t]
+#define WV(i) wvt[g * ks + 4 * (i) + t]
 #define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
@@ -350,11 +356,33 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         // accumulators in (L2-resident) global memory this touches them once per accepted move
         // instead of once per step; the registers stay with the GEMM operands.  Loads of a batch of
         // columns are issued before any store (a store may alias the next load for the compiler).
+        // wsm: the moments of the tile are staged in shared memory for the piece (whenever the problem blob leaves room:
+        // not at d = 64 with 256 data rows) -- the L2 round trip of the flush was 15 % of the warp time.
         double run = 0.0, wn = (double)(a.welford_n0 + s0);
+        if (wsm && a.welford) {
+#pragma unroll 1
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                WM(i) = (live && k < d) ? __ldcg(a.w_mean + (int64_t)k * N + gr) : 0.0;
+                WV(i) = (live && k < d) ? __ldcg(a.w_m2 + (int64_t)big_w2_index(k, d) * N + gr) : 0.0;
+            }
+        }
         auto welford_flush = [&](const bool f) {
             const bool fl = f && live && run != 0.0 && a.welford;
             if (!__any_sync(0xffffffffu, fl)) return;
             const double n1 = wn + run, c1 = run / n1, c2 = wn * c1;
+            if (wsm) {
+                if (fl) {
+#pragma unroll 1
+                    for (int i = 0; i < KQ; i++) {
+                        const double m0 = WM(i), dl = TH(i) - m0;
+                        WM(i) = fma(dl, c1, m0);
+                        WV(i) = fma(dl * dl, c2, WV(i));
+                    }
+                    wn += run; run = 0.0;
+                }
+                return;
+            }
             constexpr int B = KQ < 8 ? KQ : 8;
 #pragma unroll 1
             for (int i0 = 0; i0 < KQ; i0 += B) {
@@ -578,6 +606,10 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
                 if (k < d) a.theta[(int64_t)k * N + gr] = TH(i);
+                if (wsm && a.welford && k < d) {
+                    a.w_mean[(int64_t)k * N + gr] = WM(i);
+                    a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] = WV(i);
+                }
             }
             if (t == 0) {
                 a.logpost[gr] = lp0;
@@ -622,6 +654,8 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         }
     }
 #undef TH
+#undef WM
+#undef WV
     // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
     unsigned long long v[5] = {cnt_tr, cnt_acc, cnt_ev0, cnt_ev1, cnt_cacc};
 #pragma unroll
@@ -683,9 +717,14 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
     // warps per CTA: as many as the shared memory left by the problem blob holds (13 at d = 64 x 256, else 16)
     const bool dense_L = hh->dense_L != 0;
-    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1)), per_warp = big_warp_bytes(hh->ks, KQ, dense_L);
+    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1));
     const size_t budget = 227 * 1024;
+    // Welford moments of the tiles in shared memory when that costs no warp (and FullDiagnostics asked for them at all)
+    size_t per_warp = big_warp_bytes(hh->ks, KQ, dense_L, false);
     int warps = blob < budget ? (int)std::min<size_t>(big_max_warps(KQ), (budget - blob) / per_warp) : 0;
+    const size_t per_warp_w = big_warp_bytes(hh->ks, KQ, dense_L, true);
+    const bool wsm = a.welford && warps >= 4 && blob + (size_t)warps * per_warp_w <= budget;
+    if (wsm) per_warp = per_warp_w;
     if (warps < 4) {
         yg_set_error("large linear model: %zu bytes of G / data leave no room for the per-warp tiles", blob);
         return YG_ERR_UNSUPPORTED;
@@ -700,7 +739,7 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     // persistent grid, every CTA resident (one per SM): the balanced schedule lets warps wait on one another
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + warps - 1) / warps, e->sm_count));
     YG_CUDA_CHECK(cudaMemsetAsync(e->big_done, 0, sizeof(long long) * (size_t)tiles, st));
-    kern<<<grid, warps * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done);
+    kern<<<grid, warps * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done, wsm ? 1 : 0);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
     e->last_block = warps * 32;
