@@ -475,3 +475,25 @@ def test_dmma_acceptance_only_diagnostics_skips_the_moments_and_nothing_else():
     pre = np.concatenate([th0.T[None], x[:-1]], axis=0)
     np.testing.assert_allclose(res[0][1]["w_mean"].cpu().numpy(), pre.mean(0), rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(res[0][1]["w_m2"].cpu().numpy(), ((pre - pre.mean(0)) ** 2).sum(0), rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize("shape", [(64, 256, False), (32, 96, True), (10, 33, False)])
+def test_dmma_short_launches_compose(shape):
+    """Launches of 1, 2, 3 transitions (fewer (tile, step) units than warps, ranges inside one tile, hand-overs in every
+    launch) compose to the same chains as one launch of 6, bit for bit; ensembles smaller than a tile and than the grid."""
+    d, dd, two = shape
+    meta, arrays = bp.big_linear_problem(d, dd, 2, two_level=two, J=2)
+    for nc in (5, 2500, 20011):
+        th0 = 0.01 * np.random.default_rng(nc).standard_normal((nc, d))
+        a = _ens(meta, arrays, nc, seed=2)
+        a.set_state(th0)
+        whole = a.run(6, samples=True, accepted=True)
+        b = _ens(meta, arrays, nc, seed=2)
+        b.set_state(th0)
+        parts = [b.run(k, samples=True, accepted=True) for k in (1, 2, 3)]
+        assert torch.equal(whole["samples"], torch.cat([p["samples"] for p in parts]))
+        assert torch.equal(whole["accepted"], torch.cat([p["accepted"] for p in parts]))
+        sa, sb = a.state(), b.state()
+        assert torch.equal(sa["theta"], sb["theta"]) and torch.equal(sa["n_accept"], sb["n_accept"])
+        np.testing.assert_allclose(sa["w_mean"].cpu().numpy(), sb["w_mean"].cpu().numpy(), rtol=1e-11, atol=1e-14)
+        assert a.counters()["transitions"] == b.counters()["transitions"] == 6 * nc
