@@ -1,16 +1,27 @@
 // Dev probe: can ONE warp per sub-partition keep the FP64 pipe full with the tile product of the tensor path
-// (yagre_mcmc_b200/csrc/dmma_tile.cuh: operands out of shared memory), and what do FP64 vector instructions of other
+// (tools/probe_gemm_warp_tile.cuh: the tile product of the warp-specialised experiment, commit 285f523), and what do FP64 vector instructions of other
 // warps of the sub-partition cost it -- and what do they cost those warps?
 //   NG GEMM warps per sub-partition run misfit_tile over a 256 x 64 operand; NV "chain" warps per sub-partition run a
 //   loop of `vec_ops` FP64 vector instructions (16 independent DFMA streams) followed by `int_ops` dependent integer
 //   multiply-adds (the Philox-like part of a chain warp's work).
-// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I yagre_mcmc_b200/csrc -o tools/_build/probe_gemm_warp tools/probe_gemm_warp.cu
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/_build/probe_gemm_warp tools/probe_gemm_warp.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
-#include "dmma_tile.cuh"
+#include "probe_gemm_warp_tile.cuh"
 
 constexpr int KQ = 16, KS = 68, NP = 256;
+
+// hi and lo word of a * M (M a compile-time constant) without a high or wide multiply: four 16 x 16 -> 32 bit products
+__device__ __forceinline__ void mulhilo_16(const unsigned a, const unsigned M, unsigned &hi, unsigned &lo)
+{
+    const unsigned Mh = M >> 16, Ml = M & 0xFFFFu, ah = a >> 16, al = a & 0xFFFFu;
+    const unsigned p0 = al * Ml;
+    const unsigned mid = ah * Ml + (p0 >> 16);             // < 2^32
+    const unsigned mid2 = al * Mh + (mid & 0xFFFFu);       // < 2^32
+    hi = ah * Mh + (mid >> 16) + (mid2 >> 16);
+    lo = a * M;
+}
 
 template <int NG, int NV>
 __global__ void __launch_bounds__((NG + NV) * 128, 1) probe(double *out, long long *cyc, int iters, int vec_ops, int int_ops, int gemm_high, int int_kind, int pair)
@@ -83,6 +94,21 @@ __global__ void __launch_bounds__((NG + NV) * 128, 1) probe(double *out, long lo
                     x = ((x << 13) | (x >> 19)) + y; y = (x >> 7) ^ y;
                     x = ((x << 5) | (x >> 27)) + y; y = (x >> 11) ^ y;
                 }
+            } else if (int_kind == 5) {                 // 32 x 32 -> 64 bit products (what Philox compiles to: IMAD.WIDE.U32)
+                for (int r = 0; r < int_ops; r += 4) {
+                    const unsigned long long w0 = (unsigned long long)x * 0xD2511F53u;
+                    x = (unsigned)(w0 >> 32) ^ y; y = (unsigned)w0 + y;
+                    const unsigned long long w1 = (unsigned long long)x * 0xCD9E8D57u;
+                    x = (unsigned)(w1 >> 32) ^ y; y = (unsigned)w1 + y;
+                }
+            } else if (int_kind == 6) {                 // the same products from 16-bit halves: low multiplies only
+                for (int r = 0; r < int_ops; r += 4) {
+                    unsigned hi, lo;
+                    mulhilo_16(x, 0xD2511F53u, hi, lo);
+                    x = hi ^ y; y = lo + y;
+                    mulhilo_16(x, 0xCD9E8D57u, hi, lo);
+                    x = hi ^ y; y = lo + y;
+                }
             } else {                                    // FP32 multiply-adds
                 float fx = __uint_as_float((x & 0x007fffffu) | 0x3f800000u), fy = 0.5f;
                 for (int r = 0; r < int_ops; r += 4) {
@@ -121,13 +147,20 @@ int main(int argc, char **argv)
     double *out; long long *cyc;
     cudaMalloc(&out, 8 * 1024 * 148); cudaMalloc(&cyc, 8 * 96);
     const int iters = 200;
+    {   // the decomposition is exact
+        unsigned bad = 0, x = 12345u;
+        for (int i = 0; i < 2000000; i++) {
+            x = x * 1664525u + 1013904223u;
+            const unsigned long long w = (unsigned long long)x * 0xD2511F53u;
+            const unsigned Mh = 0xD2511F53u >> 16, Ml = 0xD2511F53u & 0xFFFFu, ah = x >> 16, al = x & 0xFFFFu;
+            const unsigned p0 = al * Ml, mid = ah * Ml + (p0 >> 16), mid2 = al * Mh + (mid & 0xFFFFu);
+            bad += (ah * Mh + (mid >> 16) + (mid2 >> 16)) != (unsigned)(w >> 32);
+        }
+        printf("16-bit decomposition of the high word: %u mismatches in 2e6\n", bad);
+    }
     run<1, 0>(out, cyc, iters, 0, 0);
     run<2, 0>(out, cyc, iters, 0, 0);
-    run<1, 0>(out, cyc, iters, 0, 0, 0, 0, 1);
-    run<2, 0>(out, cyc, iters, 0, 0, 0, 0, 1);
-    run<1, 3>(out, cyc, iters, 192, 1024, 0, 3, 0);
-    run<1, 3>(out, cyc, iters, 192, 1024, 0, 3, 1);
-    run<1, 3>(out, cyc, iters, 192, 1024, 0, 0, 1);
-    run<1, 5>(out, cyc, iters, 192, 1024, 0, 0, 1);
+    for (int kind : {3, 0, 5, 6, 1}) run<1, 3>(out, cyc, iters, 0, 1024, 0, kind);
+    for (int kind : {3, 5, 6}) run<2, 1>(out, cyc, iters, 0, 1024, 0, kind);
     return 0;
 }

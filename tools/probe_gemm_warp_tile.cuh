@@ -1,5 +1,5 @@
-// dmma_tile.cuh -- the FP64 tensor-path tile product of linear_dmma_kernel.cu (shared with tools/probe_gemm_warp.cu):
-// the weighted misfit of 8 chains against one level of the linear model as a swap-AB m16n8k4 GEMM out of shared memory.
+// probe_gemm_warp_tile.cuh -- tile products of the warp-specialised tensor-path experiment (commit 285f523), kept for
+// tools/probe_gemm_warp.cu: the weighted misfit of 8 (or 16) chains as a swap-AB m16n8k4 GEMM out of shared memory.
 #pragma once
 #include <stdint.h>
 #ifndef YG_DEVFN

@@ -6,7 +6,7 @@ import bench_problems as bp
 from yagre_mcmc_b200.ensemble import ChainEnsemble, LoweredProblem
 nc = 65536
 meta, arrays = bp.big_linear_problem(64, 256, 1)
-ens = ChainEnsemble(LoweredProblem(meta, arrays), nc, seed=1)
+ens = ChainEnsemble(LoweredProblem(meta, arrays), nc, seed=1, welford=os.environ.get("WELFORD", "1") == "1")
 mean, _ = bp.linear_gaussian_posterior(arrays, 0)
 ens.set_state(np.tile(mean, (nc, 1)))
 for _ in range(3):

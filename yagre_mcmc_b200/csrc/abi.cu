@@ -191,15 +191,14 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
                 for (int j = 0; j < d; j++) Rp[l][(size_t)i * d + j] = Lp[(size_t)j * d + i];
         }
         const size_t rows = (size_t)L.data_dim + (dense_prior[l] ? d : 0);
-        const size_t np = (rows + 31) & ~size_t(31);
+        const size_t np = (rows + 15) & ~size_t(15);
         tail_len += np * ks + np + 2 * (size_t)kp;
     }
     tail_len += 2 * (size_t)kp + (dense_L ? (size_t)kp * ks : 0);
     tail_len = (tail_len + 1) & ~size_t(1);
-    {   // the blob, the control block and the tiles of at least four chain warps (proposal tile, result slots, noise tile,
-        // + a scratch tile for a dense factor): linear_dmma_kernel.cu:big_worker_doubles
-        const size_t per_warp = sizeof(double) * (8 * (size_t)ks * (dense_L ? 2 : 1) + 64) + sizeof(float) * 8 * (size_t)(kp + 4);
-        if (sizeof(double) * (tail_len + 48) + 4 * per_warp > 226 * 1024) {
+    {   // the blob and the tiles of at least four warps (state tile, noise tile, + a scratch tile for a dense factor)
+        const size_t per_warp = sizeof(double) * 8 * (size_t)ks * (dense_L ? 2 : 1) + sizeof(float) * 8 * (size_t)(kp + 4);
+        if (sizeof(double) * tail_len + 4 * per_warp > 226 * 1024) {
             yg_set_error("large linear model: %zu bytes of G / data do not fit the shared memory of one SM", sizeof(double) * tail_len);
             return YG_ERR_UNSUPPORTED;
         }
@@ -222,7 +221,7 @@ int set_problem_big(yg_ensemble *e, const yg_problem *pb)
         const yg_level &L = pb->level[l];
         BigLevel &B = h->lvl[l];
         const int rows = L.data_dim + (dense_prior[l] ? d : 0);
-        const int np = (rows + 31) & ~31;
+        const int np = (rows + 15) & ~15;
         B.n_data = L.n_data; B.data_dim = L.data_dim; B.np = np; B.n_rows = rows;
         B.G_off = (int32_t)off;
         B.bd_off = (int32_t)(off + (size_t)np * ks);

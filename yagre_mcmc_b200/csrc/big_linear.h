@@ -7,7 +7,7 @@
 
 struct BigLevel {
     int32_t n_data, data_dim, np, n_rows;           // n_rows = rows of the GEMM operand: data_dim (+ dim when a dense prior
-                                                    // precision is folded in as extra rows); np = n_rows rounded up to 32
+                                                    // precision is folded in as extra rows); np = n_rows rounded up to 16
     int32_t G_off, bd_off, pmean_off, pprec_off;    // offsets (doubles) into the tail
     double q_const, _pad3;                          // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
 };

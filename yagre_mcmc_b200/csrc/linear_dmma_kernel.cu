@@ -45,13 +45,17 @@
 //     the FP64 pipe would cost as much as a fifth of the GEMM.
 #include "ensemble.h"
 #include "big_linear.h"
-#include "dmma_tile.cuh"
 #include <math_constants.h>
-#ifdef YG_BIG_TIMERS
-#include <cstdio>
-#endif
 
 namespace {
+
+YG_DEVFN void dmma_m16n8k4(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double b0)
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
+        : "d"(a0), "d"(a1), "d"(b0));
+}
 
 // Box-Muller on one Philox block with the TRANSFORM in FP32 (the FP32 / SFU pipes are idle next to the GEMM, the
 // FP64 pipe is not).  Same uniforms as the oracle's yo_philox_normals: u1 = m1 2^-53 in (0, 1] and u2 = k2 2^-53 in
@@ -141,6 +145,19 @@ struct NoiseSlice {
     }
 };
 
+// Shared-memory load of a GEMM operand that ptxas may not move across its neighbours.  Left to itself ptxas gathers the
+// DMMAs of one accumulator into one dependent chain (whatever the order of the PTX), and a DMMA that waits for its
+// predecessor issues every 26 cycles instead of every 16.  Volatile loads keep their program order, so the operands of
+// k-step i + 1 of ALL accumulator chains are fetched before the DMMAs of k-step i: gathering a chain would mean
+// keeping every other chain's operands alive in registers, and the scheduler keeps the interleaved order instead
+// (SASS: DMMA R28 / R32 / R36 / R24 round robin; profiles/r02_linear_dmma.md).
+YG_DEVFN double lds_ordered(const double *p)
+{
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 YG_DEVFN double quad_sum(double v)
 {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -148,72 +165,126 @@ YG_DEVFN double quad_sum(double v)
     return v;
 }
 
-// ---- synchronisation between the GEMM warps and the chain warps of a CTA (shared memory only) -----------------------
-YG_DEVFN uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-YG_DEVFN void mbar_init(uint64_t *b, uint32_t count)
+struct SmemLevel {
+    const double *G;        // [np][ks]  sqrt(w_row) G_row, w = n_data * noise precision
+    const double *bd;       // [np]      sqrt(w_row) (b - mean over the data rows)   (likelihood.py:74-75 broadcasts F against the rows)
+    const double *pmean;    // [kp]
+    const double *pprec;    // [kp]   (zero beyond dim)
+    double q_const;         // sum_col prec_col * sum_rows (d_row,col - mean_col)^2
+    int np;                 // data_dim rounded up to a multiple of 16
+};
+
+// log-posterior of the chain (column g of the warp's d x 8 tile) whose parameters are spread over the quad:
+// a[i] = theta[4 i + t].  Every lane of a quad returns the same value.
+// side.begin(pass) is called at the start of every pass over 32 (or the last 16) data rows and side.stage(i) after
+// k-step i of the pass: independent work written out between the DMMAs (the noise of the NEXT proposal; SideNone
+// for the evaluations that have none to draw).
+struct SideNone {
+    YG_DEVFN void begin(int) {}
+    YG_DEVFN void stage(int) {}
+};
+
+template <int KQ, typename SIDE>
+YG_DEVFN double logpost_tile(const SmemLevel &L, const int ks, const double (&a)[KQ], const int g, const int t, SIDE &&side)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-YG_DEVFN void mbar_arrive(uint64_t *b)          // release at CTA scope (the PTX default)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-YG_DEVFN bool mbar_try_wait(uint64_t *b, uint32_t parity)       // acquire at CTA scope; the hardware suspends the warp for a while
-{
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-    return ok != 0u;
-}
-YG_DEVFN void st_release_u32(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-YG_DEVFN uint32_t ld_acquire_u32(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
+    // sum_rows ||F - d_row||^2_P = sum_col w_col (F_col - mean_col)^2 + q_const  (exact identity; no cancellation:
+    // the row scatter is a precomputed constant).  Accumulator layout of m16n8k4 with G as the A operand:
+    // c0, c1 = F[row nb + g][chains 2t, 2t + 1], c2, c3 = F[row nb + 8 + g][the same chains].
+    double qa = 0.0, qb = 0.0;                 // partial sums of chains 2t and 2t + 1 over this lane's rows
+    auto epilogue = [&](const int nb, const double c0, const double c1, const double c2, const double c3) {
+        const double b0 = L.bd[nb + g], b1 = L.bd[nb + 8 + g];
+        const double e0 = c0 + b0, e1 = c1 + b0, e2 = c2 + b1, e3 = c3 + b1;     // sqrt(w) (A @ theta + b - mean(data))
+        qa = fma(e2, e2, fma(e0, e0, qa));
+        qb = fma(e3, e3, fma(e1, e1, qb));
+    };
+    int nb = 0, pass = 0;
+    for (; nb + 32 <= L.np; nb += 32) {        // two 16-row blocks per pass = four interleaved DMMA.8x8x4 chains
+        double c[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+        side.begin(pass++);
+        double A[2][2], An[2][2];
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            A[m][0] = lds_ordered(Gb + (size_t)(16 * m) * ks);
+            A[m][1] = lds_ordered(Gb + (size_t)(16 * m + 8) * ks);
+        }
+#pragma unroll
+        for (int i = 0; i < KQ; i++) {
+            if (i + 1 < KQ) {
+#pragma unroll
+                for (int m = 0; m < 2; m++) {
+                    An[m][0] = lds_ordered(Gb + (size_t)(16 * m) * ks + 4 * (i + 1));
+                    An[m][1] = lds_ordered(Gb + (size_t)(16 * m + 8) * ks + 4 * (i + 1));
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 2; m++) dmma_m16n8k4(c[m][0], c[m][1], c[m][2], c[m][3], A[m][0], A[m][1], a[i]);
+#pragma unroll
+            for (int m = 0; m < 2; m++) { A[m][0] = An[m][0]; A[m][1] = An[m][1]; }
+            side.stage(i);
+        }
+#pragma unroll
+        for (int m = 0; m < 2; m++) epilogue(nb + 16 * m, c[m][0], c[m][1], c[m][2], c[m][3]);
+    }
+    for (; nb < L.np; nb += 16) {              // last 16 rows: two chains
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        const double *Gb = L.G + (size_t)(nb + g) * ks + t;
+        side.begin(pass++);
+        double A0 = lds_ordered(Gb), A1 = lds_ordered(Gb + (size_t)8 * ks), B0 = 0.0, B1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < KQ; i++) {
+            if (i + 1 < KQ) {
+                B0 = lds_ordered(Gb + 4 * (i + 1));
+                B1 = lds_ordered(Gb + (size_t)8 * ks + 4 * (i + 1));
+            }
+            dmma_m16n8k4(c0, c1, c2, c3, A0, A1, a[i]);
+            A0 = B0; A1 = B1;
+            side.stage(i);
+        }
+        epilogue(nb, c0, c1, c2, c3);
+    }
+    // rows are spread over the 8 lanes that share t: butterfly over g, then every lane fetches the sum of ITS chain
+    // (chain g sits in element g & 1 of the lanes with t = g >> 1)
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        qa += __shfl_xor_sync(0xffffffffu, qa, o);
+        qb += __shfl_xor_sync(0xffffffffu, qb, o);
+    }
+    const int src = (g << 2) | (g >> 1);
+    const double va = __shfl_sync(0xffffffffu, qa, src), vb = __shfl_sync(0xffffffffu, qb, src);
+    const double q = (g & 1) ? vb : va;
+    double pr = 0.0;
+#pragma unroll
+    for (int i = 0; i < KQ; i++) {
+        const double x = a[i] - L.pmean[4 * i + t];
+        pr = fma(L.pprec[4 * i + t] * x, x, pr);
+    }
+    return -0.5 * (q + L.q_const) + (-0.5 * quad_sum(pr));
 }
 
-// CTA geometry: YG_BIG_GEMM_WARPS GEMM warps (warp w runs on sub-partition w % 4: one per FP64 pipe) and up to
-// big_max_workers(KQ) chain warps.  The register file (64 K per SM) is shared evenly by all warps of the CTA.
-#ifndef YG_BIG_GEMM_WARPS
-#define YG_BIG_GEMM_WARPS 4
+constexpr int BIG_WARPS = 16;      // most warps per CTA (8 chains each, <= 128 registers per thread); fewer when shared memory is short
+// d > 32 (KQ = 16): G of a 256-row model leaves shared memory for 13 warps; 12 are used -- three per sub-partition may
+// take 168 registers each (a fourth warp on one sub-partition caps everybody at 128: the register file is per
+// sub-partition), which the 64-parameter operand tiles need: no spills, 25.2 against 20.7 TFLOP/s with 13 x 128.
+#ifndef YG_BIG_WARPS_KQ16
+#define YG_BIG_WARPS_KQ16 12
 #endif
-#ifndef YG_BIG_WORKERS_KQ16
-#define YG_BIG_WORKERS_KQ16 12
-#endif
-#ifndef YG_BIG_WORKERS_KQ8
-#define YG_BIG_WORKERS_KQ8 20
-#endif
-#ifndef YG_BIG_WORKERS_KQ4
-#define YG_BIG_WORKERS_KQ4 24
-#endif
-constexpr int BIG_GEMM_WARPS = YG_BIG_GEMM_WARPS;
-constexpr int BIG_MAX_WORKERS = 28;         // size of the control block
-__host__ __device__ constexpr int big_max_workers(int kq)
-{
-    return kq == 16 ? YG_BIG_WORKERS_KQ16 : (kq == 8 ? YG_BIG_WORKERS_KQ8 : YG_BIG_WORKERS_KQ4);
-}
-static_assert(YG_BIG_WORKERS_KQ16 <= BIG_MAX_WORKERS && YG_BIG_WORKERS_KQ8 <= BIG_MAX_WORKERS && YG_BIG_WORKERS_KQ4 <= BIG_MAX_WORKERS, "control block");
-constexpr int BIG_CTL_DOUBLES = BIG_MAX_WORKERS + BIG_MAX_WORKERS / 2;      // done barriers (8 bytes) + request words (4 bytes)
-constexpr uint32_t REQ_EXIT = 0xFFu;
-// per chain warp: the proposal tile [8][ks] doubles (the GEMM operand), the result slots [32][2] doubles, the noise tile
-// [8][4 KQ + 4] floats of the next proposal (+ a second [8][ks] tile when the proposal factor is dense: the transpose
-// buffer of L z; + two more when the Welford moments of the tile are staged in shared memory)
+__host__ __device__ constexpr int big_max_warps(int kq) { return kq == 16 ? YG_BIG_WARPS_KQ16 : BIG_WARPS; }
+// per-warp shared memory: the state tile [8][ks] doubles and the noise tile [8][4 KQ + 4] floats of the next proposal
 __host__ __device__ constexpr int big_zs(int kq) { return 4 * kq + 4; }
-__host__ __device__ constexpr size_t big_worker_doubles(int ks, int kq, bool dense_L, bool wsm)
+// (+ a second [8][ks] tile when the proposal factor is dense: the transpose buffer of L z)
+inline size_t big_warp_bytes(int ks, int kq, bool dense_L, bool wsm)
 {
-    return 8 * (size_t)ks * (1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0)) + 64 + 4 * (size_t)big_zs(kq);
+    return sizeof(double) * 8 * (size_t)ks * (1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0)) + sizeof(float) * 8 * (size_t)big_zs(kq);
 }
 
 // FREE_NOISE = true: the production instance (Philox noise, diagonal proposal factor).  The injected / recorded noise
 // paths of the parity tests and the DENSE proposal factor (p = s + L z with L z as a second small GEMM) live in the
-// FREE_NOISE = false instance.
+// FREE_NOISE = false instance, which keeps the step loop of the production one small enough for the instruction cache
+// (stall reason no_instruction in profiles/r01_linear_dmma.md).
 template <int KQ, bool TWO_LEVEL, bool FREE_NOISE>
-__global__ void __launch_bounds__((BIG_GEMM_WARPS + big_max_workers(KQ)) * 32, 1)
-linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_done, const int wsm)
+__global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh,
+                                                                          long long *tile_done, const int wsm)
 {
     const int noise_mode = FREE_NOISE ? (int)YG_NOISE_PHILOX : a.noise_mode;
     extern __shared__ __align__(16) double smem[];
@@ -222,14 +293,6 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
     const DevBigHeader H = *gh;
     const double *gtail = reinterpret_cast<const double *>(gh + 1);
     for (int i = tid; i < H.tail_len; i += blockDim.x) smem[i] = gtail[i];
-    double *ctl = smem + ((H.tail_len + 1) & ~1);
-    uint64_t *done_bar = reinterpret_cast<uint64_t *>(ctl);                             // [BIG_MAX_WORKERS]
-    uint32_t *req = reinterpret_cast<uint32_t *>(ctl + BIG_MAX_WORKERS);               // [BIG_MAX_WORKERS]
-    const int n_workers = (blockDim.x >> 5) - BIG_GEMM_WARPS;
-    if (tid < n_workers) {
-        mbar_init(done_bar + tid, 1u);
-        req[tid] = 0u;
-    }
     __syncthreads();
     SmemLevel Lv[2];
 #pragma unroll
@@ -241,127 +304,29 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
         Lv[l].q_const = H.lvl[l].q_const;
         Lv[l].np = H.lvl[l].np;
     }
-    const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
-    constexpr int ZS = big_zs(KQ);
-    const bool dense_L = !FREE_NOISE && H.dense_L;
-    const int n_dtiles = 1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0);
-    const size_t per_worker = 8 * (size_t)ks * n_dtiles + 64 + 4 * ZS;
-    double *wbase = ctl + BIG_CTL_DOUBLES;
-
-    if (warp < BIG_GEMM_WARPS) {
-        // ================= GEMM warp: serves the chain warps wi = warp, warp + G, ... of this CTA =======================
-        // Polls their request words round robin; a request names the level, the operand is the warp's proposal tile, the
-        // answer the 64 partial sums in its result slots.  It never waits for a particular chain warp (one of them may
-        // itself be waiting for a hand-over of the balanced schedule), so the scheme cannot deadlock.
-        uint32_t alive = 0u;
-        for (int wi = warp; wi < n_workers; wi += BIG_GEMM_WARPS) alive |= 1u << wi;
-#ifdef YG_BIG_TIMERS
-        long long tm_busy = 0, tm_req = 0;
-        const long long tm_start = clock64();
-#endif
-        while (alive) {
-            bool any = false;
-#pragma unroll 1
-            for (int wi = warp; wi < n_workers; wi += BIG_GEMM_WARPS) {
-                if (!((alive >> wi) & 1u)) continue;
-                const uint32_t r = __shfl_sync(0xffffffffu, ld_acquire_u32(req + wi), 0);
-                if (r == 0u) continue;
-                if (r == REQ_EXIT) { alive &= ~(1u << wi); continue; }
-                any = true;
-#ifdef YG_BIG_TIMERS
-                const long long tm_a = clock64();
-#endif
-                double *P = wbase + (size_t)wi * per_worker, *res = P + 8 * ks * n_dtiles;
-                double b[KQ];
-#pragma unroll
-                for (int i = 0; i < KQ; i++) b[i] = P[g * ks + 4 * i + t];
-                SmemLevel L = Lv[0];
-                if (TWO_LEVEL && r == 2u) L = Lv[1];
-                double qa, qb;
-                misfit_tile<KQ>(L, ks, b, g, t, qa, qb);
-                *reinterpret_cast<double2 *>(res + 2 * lane) = make_double2(qa, qb);
-                __syncwarp();
-                if (lane == 0) {
-                    req[wi] = 0u;
-                    mbar_arrive(done_bar + wi);
-                }
-#ifdef YG_BIG_TIMERS
-                tm_busy += clock64() - tm_a;
-                tm_req++;
-#endif
-            }
-            if (!any) __nanosleep(32);
-        }
-#ifdef YG_BIG_TIMERS
-        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-            printf("cta %d gemm warp %d: total %lld busy %lld requests %lld (%.1f per request)\n", blockIdx.x, warp, clock64() - tm_start,
-                   tm_busy, tm_req, tm_req ? (double)tm_busy / tm_req : 0.0);
-#endif
-        return;
-    }
-
-    // ================= chain warp =====================================================================================
-    const int wi = warp - BIG_GEMM_WARPS;
     const double *propL = smem + H.propL_off;      // [kp] diagonal proposal factor (zero beyond dim)
     const bool pcn = H.proposal == YG_PROPOSAL_PCN;
     const double *pcn_mean = smem + H.pcn_mean_off;
+    // current state of the warp's 8 chains: [8][ks] doubles after the problem blob; lane (g, t) only ever
+    // touches its own slots (row g, columns 4 i + t), so no synchronisation is needed, and the row stride
+    // (4 mod 16 doubles) makes the accesses bank-conflict free
+    const int d = H.dim, ks = H.ks, J = TWO_LEVEL ? H.J : 1, n_lvl = TWO_LEVEL ? 2 : 1;
+    constexpr int ZS = big_zs(KQ);
+    const int n_warps = blockDim.x >> 5;
+    const bool dense_L = !FREE_NOISE && H.dense_L;
     const double *Ld = smem + H.Ld_off;            // [kp][ks] lower-triangular proposal factor (dense_L only)
-    // per-warp tiles: proposal [8][ks] (lane (g, t) only ever touches its own slots -- row g, columns 4 i + t -- and the
-    // row stride, 4 mod 16 doubles, makes the accesses bank-conflict free); (dense factor only) the transpose buffer of
-    // L z; (wsm) the Welford mean and second moment of the tile; the result slots; the noise tile [8][ZS] floats
-    double *Pt = wbase + (size_t)wi * per_worker;
-    double *scr = Pt + 8 * ks;                     // (dense_L only)
-    double *wmt = Pt + 8 * ks * (dense_L ? 2 : 1), *wvt = wmt + 8 * ks;       // (wsm only)
-    double *res = Pt + 8 * ks * n_dtiles;
-    float *zb = reinterpret_cast<float *>(res + 64);
-    uint64_t *my_done = done_bar + wi;
-    uint32_t *my_req = req + wi;
-    uint32_t phase = 0u;
+    // per-warp tiles: state [8][ks]; (dense factor only) the transpose buffer of L z [8][ks]; (wsm: when shared memory
+    // allows) the Welford mean and second moment of the tile, 2 x [8][ks]; the noise tile [8][ZS] floats
+    const int n_dtiles = 1 + (dense_L ? 1 : 0) + (wsm ? 2 : 0);
+    double *ths = smem + ((H.tail_len + 1) & ~1) + (size_t)warp * (8 * ks * n_dtiles + 4 * ZS);   // 8 ZS floats = 4 ZS doubles
+    double *scr = ths + 8 * ks;                    // (dense_L only)
+    double *wmt = ths + 8 * ks * (dense_L ? 2 : 1), *wvt = wmt + 8 * ks;      // (wsm only)
+    float *zb = reinterpret_cast<float *>(ths + 8 * ks * n_dtiles);
 #define WM(i) wmt[g * ks + 4 * (i) + t]
 #define WV(i) wvt[g * ks + 4 * (i) + t]
-#define PT(i) Pt[g * ks + 4 * (i) + t]
+#define TH(i) ths[g * ks + 4 * (i) + t]
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
-
-    // the proposal tile is complete: hand it to the GEMM warp
-    auto submit = [&](const uint32_t code) {
-        __syncwarp();
-        if (lane == 0) st_release_u32(my_req, code);
-    };
-    // wait for the answer; sum the row lanes' partial sums of THIS lane's chain in the order of a butterfly over g
-    // (chain g is element g & 1 of the lanes with t' = g >> 1: slots 8 g' + g)
-#ifdef YG_BIG_TIMERS
-    long long tm_wait = 0, tm_evals = 0, tm_ph[6] = {0, 0, 0, 0, 0, 0}, tm_mark = clock64();      // propose, noise, prior, accept, flush, rest
-    const long long tm_start = clock64();
-#define TM_PHASE(k) { const long long tm_now = clock64(); tm_ph[k] += tm_now - tm_mark; tm_mark = tm_now; }
-#else
-#define TM_PHASE(k)
-#endif
-    auto collect = [&]() {
-#ifdef YG_BIG_TIMERS
-        const long long tm_a = clock64();
-#endif
-        while (!mbar_try_wait(my_done, phase)) {}
-#ifdef YG_BIG_TIMERS
-        tm_wait += clock64() - tm_a;
-        tm_evals++;
-        tm_mark = clock64();
-#endif
-        phase ^= 1u;
-        const double *r = res + g;
-        const double v0 = r[0], v1 = r[8], v2 = r[16], v3 = r[24], v4 = r[32], v5 = r[40], v6 = r[48], v7 = r[56];
-        return ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
-    };
-    // prior term of the point in the proposal tile (every lane of a quad returns the same value)
-    auto prior_of_tile = [&](const SmemLevel &L) {
-        double pr = 0.0;
-#pragma unroll
-        for (int i = 0; i < KQ; i++) {
-            const double x = PT(i) - L.pmean[4 * i + t];
-            pr = fma(L.pprec[4 * i + t] * x, x, pr);
-        }
-        return -0.5 * quad_sum(pr);
-    };
 
     // ---- one piece of work: transitions [s0, s1) of the 8 chains of `tile` -------------------------------------
     auto run_piece = [&](const int64_t tile, const int64_t s0, const int64_t s1) {
@@ -377,12 +342,10 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
             __syncwarp();
             __threadfence();
         }
-        // current state of the chain, spread over the quad: th[i] = theta[4 i + t]
-        double th[KQ];
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < KQ; i++) {
             const int k = 4 * i + t;
-            th[i] = (k < d) ? __ldcg(a.theta + (int64_t)k * N + gg) : 0.0;
+            TH(i) = (k < d) ? __ldcg(a.theta + (int64_t)k * N + gg) : 0.0;
         }
         double lp0 = __ldcg(a.logpost + gg), lp1 = TWO_LEVEL ? __ldcg(a.logpost + N + gg) : 0.0;
         unsigned long long nacc = __ldcg(a.n_accept + gg);
@@ -391,9 +354,10 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
         // consecutive steps contributes  n' = n + m, mean' = mean + (x - mean) m / n',
         // M2' = M2 + (x - mean)^2 n m / n'  -- algebraically the m sequential updates.  With the
         // accumulators in (L2-resident) global memory this touches them once per accepted move
-        // instead of once per step.  Loads of a batch of columns are issued before any store (a store may alias the
-        // next load for the compiler).
-        // wsm: the moments of the tile are staged in shared memory for the piece (whenever the problem blob leaves room).
+        // instead of once per step; the registers stay with the GEMM operands.  Loads of a batch of
+        // columns are issued before any store (a store may alias the next load for the compiler).
+        // wsm: the moments of the tile are staged in shared memory for the piece (whenever the problem blob leaves room:
+        // not at d = 64 with 256 data rows) -- the L2 round trip of the flush was 15 % of the warp time.
         double run = 0.0, wn = (double)(a.welford_n0 + s0);
         if (wsm && a.welford) {
 #pragma unroll 1
@@ -409,9 +373,9 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
             const double n1 = wn + run, c1 = run / n1, c2 = wn * c1;
             if (wsm) {
                 if (fl) {
-#pragma unroll
+#pragma unroll 1
                     for (int i = 0; i < KQ; i++) {
-                        const double m0 = WM(i), dl = th[i] - m0;
+                        const double m0 = WM(i), dl = TH(i) - m0;
                         WM(i) = fma(dl, c1, m0);
                         WV(i) = fma(dl * dl, c2, WV(i));
                     }
@@ -420,7 +384,7 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                 return;
             }
             constexpr int B = KQ < 8 ? KQ : 8;
-#pragma unroll
+#pragma unroll 1
             for (int i0 = 0; i0 < KQ; i0 += B) {
                 double m0[B], v0[B];
 #pragma unroll
@@ -434,7 +398,7 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                 for (int i = 0; i < B; i++) {
                     const int k = 4 * (i0 + i) + t;
                     if (fl && k < d) {
-                        const double dl = th[i0 + i] - m0[i];
+                        const double dl = TH(i0 + i) - m0[i];
                         a.w_mean[(int64_t)k * N + gr] = fma(dl, c1, m0[i]);
                         a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] = fma(dl * dl, c2, v0[i]);
                     }
@@ -447,42 +411,49 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
         // Columns 4i+t and 4i+(t^1) of a lane pair are the two halves of pair b = (4i + (t & ~1)) / 2: the even lane
         // draws the pairs of even i, the odd lane those of odd i -- one Philox block + one Box-Muller per lane and 4
         // parameters -- and both halves go to the warp's noise tile, from where every lane later picks its columns.
-        // The noise does not depend on the chain state (counter-based Philox): it is drawn while the GEMM warp works on
-        // the evaluation that precedes the proposal.
+        // Slice `it` (of KQ / 2) is one pair per lane; the slices are drawn INSIDE the GEMM loop of the evaluation that
+        // precedes the proposal (the noise does not depend on the chain state: counter-based Philox).
         NoiseSlice ns;
-        auto gen_noise = [&](const int64_t n, const int j) {
-            if (noise_mode == YG_NOISE_INJECT) return;
-#pragma unroll 1
-            for (int it = 0; it < KQ / 2; it++) {
-                const int i_mine = 2 * it + odd;
-                ns.begin(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)((4 * i_mine + (t & ~1)) >> 1),
-                         reinterpret_cast<float2 *>(zb + g * ZS + 4 * i_mine + (t & ~1)), true);
-                ns.all();
-            }
+        auto slice_begin = [&](const int64_t n, const int j, const int it, const bool on) {
+            // a slice index beyond KQ / 2 (more passes than slices) redraws an earlier slice: same values, same place
+            const int i_mine = 2 * (it & (KQ / 2 - 1)) + odd;
+            ns.begin(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)((4 * i_mine + (t & ~1)) >> 1),
+                     reinterpret_cast<float2 *>(zb + g * ZS + 4 * i_mine + (t & ~1)), on && noise_mode != YG_NOISE_INJECT);
+        };
+        auto gen_noise = [&](const int64_t n, const int j, const int it) {       // one slice, not interleaved with anything
+            slice_begin(n, j, it, true);
+            ns.all();
+        };
+        struct SideNoise {
+            decltype(slice_begin) &sb;
+            NoiseSlice &ns;
+            int64_t n;
+            int j;
+            bool on;
+            YG_DEVFN void begin(const int pass) { sb(n, j, pass, on); }
+            YG_DEVFN void stage(const int i) { ns.template stage<KQ>(i); }
         };
         // the proposal after (n, j) in the order the chain consumes them; n == s1 means "none in this piece"
-        auto draw_next = [&](int64_t n, int j) {
+        auto next_of = [&](int64_t &n, int &j) {
             if (++j == J) { j = 0; n++; }
-            if (n < s1) gen_noise(n, j);
         };
         // p = s + L z with a diagonal L, unfused like numpy.  pCN (pcn.py:30-35): p = sqrt(1 - 2h) s + sqrt(2h) (m + L z).
-        // The proposal goes straight into the proposal tile (the GEMM operand).
-        auto propose = [&](const double (&src)[KQ], int64_t n, int j) {
+        auto propose = [&](auto &&src, int64_t n, int j, double (&p)[KQ]) {
             bool same = true;
             __syncwarp();                                  // the noise tile was written by other lanes
-            if (dense_L) {
-                double zv[KQ];
+            double zv[KQ];
 #pragma unroll
-                for (int i = 0; i < KQ; i++) {
-                    const int k = 4 * i + t;
-                    zv[i] = 0.0;
-                    if (noise_mode == YG_NOISE_INJECT) {
-                        if (k < d) zv[i] = a.z[((n * J + j) * d + k) * N + gg];
-                    } else if (k < d) {
-                        zv[i] = (double)zb[g * ZS + k];
-                        if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[i];
-                    }
+            for (int i = 0; i < KQ; i++) {
+                const int k = 4 * i + t;
+                zv[i] = 0.0;
+                if (noise_mode == YG_NOISE_INJECT) {
+                    if (k < d) zv[i] = a.z[((n * J + j) * d + k) * N + gg];
+                } else if (k < d) {
+                    zv[i] = (double)zb[g * ZS + k];
+                    if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[i];
                 }
+            }
+            if (dense_L) {
                 // L z of the 8 chains as a GEMM: L is the A operand (16 rows x 4 columns per mma), z -- already in the
                 // B-fragment layout -- the other one; only the k-steps of the lower triangle are issued.  The accumulators
                 // hold (L z)[row][chain]; the scratch tile transposes them back to "lane (g, t) holds chain g, row 4i + t".
@@ -502,39 +473,28 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
 #pragma unroll
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
-                double lz;
-                if (dense_L) lz = scr[g * ks + k];
-                else {
-                    double zv = 0.0;
-                    if (noise_mode == YG_NOISE_INJECT) {
-                        if (k < d) zv = a.z[((n * J + j) * d + k) * N + gg];
-                    } else if (k < d) {
-                        zv = (double)zb[g * ZS + k];
-                        if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv;
-                    }
-                    lz = __dmul_rn(propL[k], zv);
-                }
-                const double sv = src[i];
-                const double p = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[k], lz))) : __dadd_rn(sv, lz);
-                PT(i) = p;
-                same = same && (p == sv);
+                const double sv = src(i);
+                const double lz = dense_L ? scr[g * ks + k] : __dmul_rn(propL[k], zv[i]);
+                p[i] = pcn ? __dadd_rn(__dmul_rn(H.pcn_a, sv), __dmul_rn(H.pcn_b, __dadd_rn(pcn_mean[k], lz))) : __dadd_rn(sv, lz);
+                same = same && (p[i] == sv);
             }
+            __syncwarp();                                  // every lane has read its columns: the tiles may be refilled
             // parameter/vector.py:37-45: equal iff every coordinate is equal (all four lanes agree)
             const unsigned m = __ballot_sync(0xffffffffu, same);
             return ((m >> (4 * g)) & 0xFu) == 0xFu;
         };
-        // log-posterior on level 0 of the proposal in the tile, while the noise of the following proposal is drawn
-        auto eval_and_draw = [&](const int64_t n, const int j) {
-            submit(1u);                                    // (its __syncwarp: every lane has read its noise columns)
-            TM_PHASE(0)
-            draw_next(n, j);
-            TM_PHASE(1)
-            const double pr = prior_of_tile(Lv[0]);
-            TM_PHASE(2)
-            const double q = collect();
-            return -0.5 * (q + Lv[0].q_const) + pr;
+        // log-posterior of proposal (n, j) on level 0 while the noise of the following proposal is drawn
+        auto eval_and_draw = [&](const double (&p)[KQ], int64_t n, int j) {
+            next_of(n, j);
+            const bool more = n < s1;
+            if (!more) n = s1 - 1;                                                 // a valid counter; nothing is stored
+            const double lp = logpost_tile<KQ>(Lv[0], ks, p, g, t, SideNoise{slice_begin, ns, n, j, more});
+            const int passes = (Lv[0].np + 31) >> 5;
+            if (more)
+                for (int it = passes; it < KQ / 2; it++) gen_noise(n, j, it);       // few data rows: the rest of the slices
+            return lp;
         };
-        gen_noise(s0, 0);                                                          // the first proposal of the piece
+        for (int it = 0; it < KQ / 2; it++) gen_noise(s0, 0, it);                 // the first proposal of the piece
 
         int64_t thin_left = a.thin - (s0 % a.thin), thin_out = s0 / a.thin - 1;      // once per piece, not per step
         for (int64_t n = s0; n < s1; n++) {
@@ -545,33 +505,33 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
             // this step is seen once more; the accumulators are touched when the state changes.
             run += 1.0;
             bool accepted = false;
-            TM_PHASE(5)
             if (!TWO_LEVEL) {
-                const bool eq = propose(th, n, 0);
-                double u = 0.0;
-                if (!eq && noise_mode != YG_NOISE_INJECT) u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
-                const double lpp = eval_and_draw(n, 0);
+                double p[KQ];
+                const bool eq = propose([&](int i) { return TH(i); }, n, 0, p);
+                const double lpp = eval_and_draw(p, n, 0);
                 if (!eq) {                                              // metropolisHastings.py:60-61
                     if (t == 0 && live) cnt_ev0++;
+                    double u;
                     if (noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
-                    else if (noise_mode == YG_NOISE_RECORD && live && t == 0) a.u_f[n * N + gg] = u;
+                    else {
+                        u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                        if (noise_mode == YG_NOISE_RECORD && live && t == 0) a.u_f[n * N + gg] = u;
+                    }
                     accepted = accept_rule(lpp - lp0, u);
                 }
-                TM_PHASE(3)
                 welford_flush(accepted);
-                TM_PHASE(4)
                 if (accepted) {
 #pragma unroll
-                    for (int i = 0; i < KQ; i++) th[i] = PT(i);
+                    for (int i = 0; i < KQ; i++) TH(i) = p[i];
                     lp0 = lpp;
                 }
             } else {
-                double s[KQ], lps = lp0;
+                double s[KQ], p[KQ], lps = lp0;
 #pragma unroll
-                for (int i = 0; i < KQ; i++) s[i] = th[i];
+                for (int i = 0; i < KQ; i++) s[i] = TH(i);
                 for (int j = 0; j < J; j++) {                           // coarse sub-chain, mlda.py:100-110
-                    const bool eq = propose(s, n, j);
-                    const double lpp = eval_and_draw(n, j);
+                    const bool eq = propose([&](int i) { return s[i]; }, n, j, p);
+                    const double lpp = eval_and_draw(p, n, j);
                     if (eq) continue;
                     if (t == 0 && live) cnt_ev0++;
                     const int64_t ui = (n * J + j) * N + gg;
@@ -583,7 +543,7 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                     }
                     if (accept_rule(lpp - lps, u)) {
 #pragma unroll
-                        for (int i = 0; i < KQ; i++) s[i] = PT(i);
+                        for (int i = 0; i < KQ; i++) s[i] = p[i];
                         lps = lpp;
                         if (t == 0 && live) cnt_cacc++;
                     }
@@ -593,23 +553,20 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                 // the 8 chains moved, and only the chains that moved use (and count) its result.
                 bool same = true;
 #pragma unroll
-                for (int i = 0; i < KQ; i++) same = same && (s[i] == th[i]);
+                for (int i = 0; i < KQ; i++) same = same && (s[i] == TH(i));
                 const unsigned m = __ballot_sync(0xffffffffu, same);
                 const bool moved = (((m >> (4 * g)) & 0xFu) != 0xFu) && live;
                 double lpf = 0.0;
                 if (__any_sync(0xffffffffu, moved)) {
-#pragma unroll
-                    for (int i = 0; i < KQ; i++) PT(i) = s[i];
-                    submit(2u);
-                    double u = 0.0;
-                    if (moved && noise_mode != YG_NOISE_INJECT) u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
-                    const double pr = prior_of_tile(Lv[1]);
-                    const double q = collect();
-                    lpf = -0.5 * (q + Lv[1].q_const) + pr;
+                    lpf = logpost_tile<KQ>(Lv[1], ks, s, g, t, SideNone{});
                     if (moved) {
                         if (t == 0) cnt_ev1++;
+                        double u;
                         if (noise_mode == YG_NOISE_INJECT) u = a.u_f[n * N + gg];
-                        else if (noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
+                        else {
+                            u = philox_uniform(a.seed, gid, step, YG_SUB_FINE);
+                            if (noise_mode == YG_NOISE_RECORD && t == 0) a.u_f[n * N + gg] = u;
+                        }
                         const double delta = lpf + lp0 - lps - lp1;     // mlda.py:148-152, this order
                         accepted = accept_rule(delta, u);
                     }
@@ -617,7 +574,7 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                 welford_flush(accepted);
                 if (accepted) {
 #pragma unroll
-                    for (int i = 0; i < KQ; i++) th[i] = s[i];
+                    for (int i = 0; i < KQ; i++) TH(i) = s[i];
                     lp0 = lps;
                     lp1 = lpf;
                 }
@@ -631,9 +588,9 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
                 if (store_now) {
                     const int64_t o = thin_out;
                     if (a.samples) {
-#pragma unroll
+#pragma unroll 1
                         for (int i = 0; i < KQ; i++)
-                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr] = th[i];
+                            if (4 * i + t < d) a.samples[(o * d + 4 * i + t) * N + gr] = TH(i);
                     }
                     if (a.lp_out && t == 0) {
                         a.lp_out[(o * n_lvl) * N + gr] = lp0;
@@ -645,10 +602,10 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
         // ---- store chain state ------------------------------------------------------------------
         welford_flush(true);
         if (live) {
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
-                if (k < d) a.theta[(int64_t)k * N + gr] = th[i];
+                if (k < d) a.theta[(int64_t)k * N + gr] = TH(i);
                 if (wsm && a.welford && k < d) {
                     a.w_mean[(int64_t)k * N + gr] = WM(i);
                     a.w_m2[(int64_t)big_w2_index(k, d) * N + gr] = WV(i);
@@ -668,20 +625,21 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
     };
 
     // ---- balanced schedule: this warp's contiguous range of the (tile-major, step-minor) work list ------------------
-    // A chain warp only ever waits for the chain warp with the next lower global index (same CTA or the CTA with the next
-    // lower blockIdx), which never waits for a higher one: with CTAs dispatched in index order nothing can wait for a CTA
-    // that is not resident yet, even if the grid shares the GPU with other work.
+    // A warp only ever waits for the warp with the next lower global index (same CTA or the CTA with the next lower
+    // blockIdx), which never waits for a higher one: with CTAs dispatched in index order nothing can wait for a CTA that
+    // is not resident yet, even if the grid shares the GPU with other work.
     const int64_t n_tiles = (N + 7) / 8, S = a.n_steps;
-    const int64_t gw = (int64_t)blockIdx.x * n_workers + wi, GW = (int64_t)gridDim.x * n_workers;
+    const int64_t gw = (int64_t)blockIdx.x * n_warps + warp, GW = (int64_t)gridDim.x * n_warps;
     // ranges in units of transitions: [lo, hi); n_tiles * S < 2^63 / GW for every admissible size
     const int64_t U = n_tiles * S;
     const int64_t lo = (U / GW) * gw + ((U % GW) * gw) / GW, hi = (U / GW) * (gw + 1) + ((U % GW) * (gw + 1)) / GW;
     if (lo < hi) {
         const int64_t t_first = lo / S, s_first = lo - t_first * S;
         const int64_t t_last = (hi - 1) / S, s_end = hi - t_last * S;          // transitions [.., s_end) of the last tile
-        // Pieces in the order they are run (ONE call site of the step loop): the head of the last tile (it has no
-        // predecessor, so it can always run), the whole tiles, and last the tail of the first tile -- it waits for the
-        // previous warp's head, which that warp ran FIRST.  A range inside one tile is a single piece.
+        // Pieces in the order they are run (ONE call site: the step loop must not be inlined several times, it would
+        // no longer fit the instruction cache): the head of the last tile (it has no predecessor, so it can always
+        // run), the whole tiles, and last the tail of the first tile -- it waits for the previous warp's head, which
+        // that warp ran FIRST.  A range inside one tile is a single piece.
         const bool single = t_first == t_last;
         const int64_t has_head = (!single && s_end < S) ? 1 : 0, has_tail = (!single && s_first > 0) ? 1 : 0;
         const int64_t w_lo = t_first + has_tail, n_whole = single ? 0 : (t_last + (s_end == S ? 1 : 0)) - w_lo;
@@ -695,15 +653,7 @@ linear_dmma_mh_kernel(const RunArgs a, const DevBigHeader *gh, long long *tile_d
             run_piece(tile, s0, s1);
         }
     }
-    submit(REQ_EXIT);                              // this warp asks for nothing more
-#ifdef YG_BIG_TIMERS
-    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
-        printf("cta %d chain warp %d: total %lld waiting %lld evaluations %lld (%.1f own work per evaluation): propose %lld noise %lld prior %lld accept %lld flush %lld rest %lld\n", blockIdx.x, wi,
-               clock64() - tm_start, tm_wait, tm_evals, tm_evals ? (double)(clock64() - tm_start - tm_wait) / tm_evals : 0.0,
-               tm_ph[0] / tm_evals, tm_ph[1] / tm_evals, tm_ph[2] / tm_evals, tm_ph[3] / tm_evals, tm_ph[4] / tm_evals, tm_ph[5] / tm_evals);
-#endif
-#undef PT
-#undef TM_PHASE
+#undef TH
 #undef WM
 #undef WV
     // ---- counters: warp-shuffle reduction, one atomic per warp ----------------------------------
@@ -765,21 +715,21 @@ template <int KQ>
 int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
 {
     const DevBigHeader *hh = reinterpret_cast<const DevBigHeader *>(e->h_problem.data());
-    // chain warps per CTA: as many as the shared memory left by the problem blob holds (12 at d = 64 x 256)
+    // warps per CTA: as many as the shared memory left by the problem blob holds (13 at d = 64 x 256, else 16)
     const bool dense_L = hh->dense_L != 0;
-    const size_t blob = sizeof(double) * ((((size_t)hh->tail_len + 1) & ~size_t(1)) + BIG_CTL_DOUBLES);
+    const size_t blob = sizeof(double) * (((size_t)hh->tail_len + 1) & ~size_t(1));
     const size_t budget = 227 * 1024;
     // Welford moments of the tiles in shared memory when that costs no warp (and FullDiagnostics asked for them at all)
-    size_t per_worker = sizeof(double) * big_worker_doubles(hh->ks, KQ, dense_L, false);
-    const int workers = blob < budget ? (int)std::min<size_t>(big_max_workers(KQ), (budget - blob) / per_worker) : 0;
-    const size_t per_worker_w = sizeof(double) * big_worker_doubles(hh->ks, KQ, dense_L, true);
-    const bool wsm = a.welford && workers >= BIG_GEMM_WARPS && blob + (size_t)workers * per_worker_w <= budget;
-    if (wsm) per_worker = per_worker_w;
-    if (workers < BIG_GEMM_WARPS) {
+    size_t per_warp = big_warp_bytes(hh->ks, KQ, dense_L, false);
+    int warps = blob < budget ? (int)std::min<size_t>(big_max_warps(KQ), (budget - blob) / per_warp) : 0;
+    const size_t per_warp_w = big_warp_bytes(hh->ks, KQ, dense_L, true);
+    const bool wsm = a.welford && warps >= 4 && blob + (size_t)warps * per_warp_w <= budget;
+    if (wsm) per_warp = per_warp_w;
+    if (warps < 4) {
         yg_set_error("large linear model: %zu bytes of G / data leave no room for the per-warp tiles", blob);
         return YG_ERR_UNSUPPORTED;
     }
-    const size_t smem = blob + (size_t)workers * per_worker;
+    const size_t smem = blob + (size_t)warps * per_warp;
     const bool free_noise = a.noise_mode == YG_NOISE_PHILOX && !dense_L;      // the general instance also knows dense factors
     auto kern = e->cfg.n_levels == 2
                     ? (free_noise ? linear_dmma_mh_kernel<KQ, true, true> : linear_dmma_mh_kernel<KQ, true, false>)
@@ -787,13 +737,12 @@ int launch_t(yg_ensemble *e, const RunArgs &a, cudaStream_t st)
     YG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = (a.n_chains + 7) / 8;
     // persistent grid, every CTA resident (one per SM): the balanced schedule lets warps wait on one another
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + workers - 1) / workers, e->sm_count));
-    const int block = (BIG_GEMM_WARPS + workers) * 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + warps - 1) / warps, e->sm_count));
     YG_CUDA_CHECK(cudaMemsetAsync(e->big_done, 0, sizeof(long long) * (size_t)tiles, st));
-    kern<<<grid, block, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done, wsm ? 1 : 0);
+    kern<<<grid, warps * 32, smem, st>>>(a, reinterpret_cast<const DevBigHeader *>(e->d_problem), e->big_done, wsm ? 1 : 0);
     YG_CUDA_CHECK(cudaGetLastError());
     e->last_grid = grid;
-    e->last_block = block;
+    e->last_block = warps * 32;
     e->last_smem = (int)smem;
     e->launches += 1;
     return YG_OK;
