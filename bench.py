@@ -690,6 +690,37 @@ def measure_other_configs(device, fp64_peak, main_value, hbm_peak_gbs):
     out["C3_linear_two_level_16384"] = small_entry("C3", ms, c, 2, sms, 5000, 16384,
                                                    "generic_mh_kernel<2,2,true> (warp-specialised: producer / consumer warps)")
     ens.close()
+    # C3 with the adaptive error model of the same example (example_inference_linearModel_twoLevel.py:180-250,
+    # chain/method/aem.py): per-chain error-model moments and the LRU(3) cache of the coarse likelihood in the step loop
+    ens = ChainEnsemble(LoweredProblem(meta, arrays), 16384, device=device, seed=5, aem=dict(min_data=8, heuristic=True))
+    ens.set_state(np.zeros((16384, 2)))
+    ms, c = timed(ens, 5000)
+    out["C3_linear_two_level_aem_16384"] = {
+        "chain_steps_per_s": c["transitions"] / ms * 1e3, "accept_rate": c["accepted"] / c["transitions"],
+        "coarse_evals_per_step": c["coarse_evals"] / c["transitions"], "fine_evals_per_step": c["fine_evals"] / c["transitions"],
+        "kernel": "aem_mh_kernel (adaptive error model, min_data 8, noise-scaling heuristic)",
+        "vs_plain_two_level": (c["transitions"] / ms * 1e3) / out["C3_linear_two_level_16384"]["chain_steps_per_s"]}
+    ens.close()
+    # ESS/s of C3 with and without the adaptive error model (the error model lifts the acceptance of
+    # the example and cuts its IAT): 16,384 chains x 20,000 transitions thinned by 4, burn-in 1,000, IAT on the device
+    c3 = {}
+    for label, aem in (("two_level", None), ("two_level_aem", dict(min_data=8, heuristic=True))):
+        ens = ChainEnsemble(LoweredProblem(meta, arrays), 16384, device=device, seed=6, aem=aem)
+        ens.set_state(np.zeros((16384, 2)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        smp = ens.run(20000, thin=4, samples=True)["samples"]
+        e1.record()
+        torch.cuda.synchronize()
+        iat, ess_c = iat_ess(smp[250:], "max")            # in units of stored (every 4th) states
+        c3[label] = {"ess_per_s": float(ess_c.sum().item()) / (e0.elapsed_time(e1) * 1e-3),
+                     "mean_iat_max_transitions": 4.0 * float(iat.double().mean().item()),
+                     "degenerate_chains": int((ess_c == 0).sum().item()),
+                     "chain_steps_per_s": 16384 * 20000 / (e0.elapsed_time(e1) * 1e-3)}
+        del smp
+        ens.close()
+    c3["aem_over_plain"] = c3["two_level_aem"]["ess_per_s"] / c3["two_level"]["ess_per_s"]
+    out["C3_ess_16384x20000"] = c3
     # C2: 2-D Gaussian target, per-chain adaptive Metropolis, 4,096 chains
     meta, arrays = bp.gauss2d_problem()
     ens = ChainEnsemble(LoweredProblem(meta, arrays), 4096, device=device, seed=5,
