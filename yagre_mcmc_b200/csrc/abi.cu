@@ -892,3 +892,17 @@ extern "C" int yg_fp64_tensor_peak(int32_t device, double ms, double *tflops_out
     if (!tflops_out) return YG_ERR_INVALID;
     return yg_dmma_peak(device, ms, tflops_out);
 }
+
+#ifdef YG_BOUNDS_CHECK
+// Bounds-checked development build only (not part of include/yagre_b200.h): proves that YG_CHK is live in THIS
+// library by violating it on purpose.  Returns 1 when the device assert fired (the CUDA context is unusable
+// afterwards: call it last, in a process of its own), 0 when the launch completed, i.e. the checks are compiled out.
+namespace {
+__global__ void bounds_selftest_kernel(int limit) { YG_CHK(threadIdx.x + 1, limit); }
+}  // namespace
+extern "C" int yg_bounds_check_selftest(void)
+{
+    bounds_selftest_kernel<<<1, 32>>>(1);
+    return cudaDeviceSynchronize() == cudaErrorAssert ? 1 : 0;
+}
+#endif

@@ -12,6 +12,23 @@
 
 #define YG_DEVFN __device__ __forceinline__
 
+// Bounds-checked development build (`make -C yagre_mcmc_b200/csrc checked`, -DYG_BOUNDS_CHECK): every computed index
+// into a shared-memory carve-up or a caller-provided device buffer is asserted against the extent of that array
+// (compute-sanitizer is not available on the B200 pool, profiles/r02_summary.md).  In the product build the macro
+// expands to nothing and the SASS is unchanged.
+#ifdef YG_BOUNDS_CHECK
+#include <cassert>
+#define YG_CHK(idx, limit) assert((long long)(idx) >= 0 && (long long)(idx) < (long long)(limit))
+YG_DEVFN uint32_t yg_dynamic_smem_bytes()
+{
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+    return v;
+}
+#else
+#define YG_CHK(idx, limit) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------
 // Device problem blob: one contiguous, 16-byte aligned buffer per handle that
 // kernels stage into shared memory (one TMA bulk copy in the LV kernel).

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
             double z0 = 0.0, z1 = 0.0, u;
             if (!TWO_LEVEL || j < J) philox_normal_pair(a.seed, gid, step, (uint32_t)j, 0u, z0, z1);
             u = philox_uniform(a.seed, gid, step, (!TWO_LEVEL || j == J) ? YG_SUB_FINE : (uint32_t)j);
+            YG_CHK((q % WS_RING) * 96 + ws_lane + 64, WS_RING * 96);
             double *slot = ws_ring + (q % WS_RING) * 96 + ws_lane;
             slot[0] = z0; slot[32] = z1; slot[64] = u;
             __threadfence_block();
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
         const int e = (int)(ws_q % WS_RING);
         while (ws_ready[e] != ws_q + 1ull) { }
         __threadfence_block();
+        YG_CHK(e * 96 + ws_lane + 64, WS_RING * 96);
         const volatile double *slot = ws_ring + e * 96 + ws_lane;
         ws_z0 = slot[0]; ws_z1 = slot[32]; ws_u = slot[64];
         __syncwarp(ws_mask);
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
                 for (int i = 0; i < D; i++) z[i] = (i == 0) ? ws_z0 : (i == 1 ? ws_z1 : 0.0);
             } else if (a.noise_mode == YG_NOISE_INJECT) {
 #pragma unroll
+                YG_CHK(((n * J + j) * d + d - 1) * N + g, a.n_steps * J * d * N);
                 for (int i = 0; i < D; i++) z[i] = (i < d) ? a.z[((n * J + j) * d + i) * N + g] : 0.0;
             } else {
 #pragma unroll
@@ -473,9 +476,11 @@ __global__ void __launch_bounds__(WS ? WS_THREADS : 128) generic_mh_kernel(const
             if (accepted) { nacc++; cnt_acc++; }
             cnt_tr++;
             if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+            YG_CHK(g, N); YG_CHK(n, a.n_steps);
             if (--thin_left == 0) {                 // (n + 1) % thin == 0 without a 64-bit division per step
                 thin_left = a.thin;
                 const int64_t o = thin_out++;
+                YG_CHK(o, a.n_steps / a.thin);
                 if (a.samples) {
 #pragma unroll
                     for (int i = 0; i < D; i++)
@@ -718,6 +723,7 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
             for (int i = 0; i < D; i++) z[i] = 0.0;
             if (a.noise_mode == YG_NOISE_INJECT) {
 #pragma unroll
+                YG_CHK(((n * J + j) * d + d - 1) * N + g, a.n_steps * J * d * N);
                 for (int i = 0; i < D; i++) z[i] = (i < d) ? a.z[((n * J + j) * d + i) * N + g] : 0.0;
             } else {
 #pragma unroll
@@ -841,9 +847,11 @@ __global__ void __launch_bounds__(128) aem_mh_kernel(const RunArgs a)
             if (accepted) { nacc++; cnt_acc++; }
             cnt_tr++;
             if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+            YG_CHK(g, N); YG_CHK(n, a.n_steps);
             if (--thin_left == 0) {                 // (n + 1) % thin == 0 without a 64-bit division per step
                 thin_left = a.thin;
                 const int64_t o = thin_out++;
+                YG_CHK(o, a.n_steps / a.thin);
                 if (a.samples) {
 #pragma unroll
                     for (int i = 0; i < D; i++)

@@ -322,9 +322,21 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
     double *scr = ths + 8 * ks;                    // (dense_L only)
     double *wmt = ths + 8 * ks * (dense_L ? 2 : 1), *wvt = wmt + 8 * ks;      // (wsm only)
     float *zb = reinterpret_cast<float *>(ths + 8 * ks * n_dtiles);
+#ifdef YG_BOUNDS_CHECK
+    // every per-warp tile is [8][ks] doubles; the warp's region must end inside the dynamic shared memory of the launch
+    YG_CHK(reinterpret_cast<unsigned char *>(zb + 8 * ZS) - reinterpret_cast<unsigned char *>(smem) - 1, yg_dynamic_smem_bytes());
+    auto tile_at = [&](double *tile, const int i) -> double & {
+        YG_CHK(g * ks + 4 * i + t, 8 * ks);
+        return tile[g * ks + 4 * i + t];
+    };
+#define WM(i) tile_at(wmt, (i))
+#define WV(i) tile_at(wvt, (i))
+#define TH(i) tile_at(ths, (i))
+#else
 #define WM(i) wmt[g * ks + 4 * (i) + t]
 #define WV(i) wvt[g * ks + 4 * (i) + t]
 #define TH(i) ths[g * ks + 4 * (i) + t]
+#endif
     const int64_t N = a.n_chains;
     unsigned long long cnt_acc = 0ull, cnt_ev0 = 0ull, cnt_ev1 = 0ull, cnt_tr = 0ull, cnt_cacc = 0ull;
 
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         const bool live = gr < N;
         const int64_t gg = live ? gr : 0;
         const uint64_t gid = (uint64_t)(a.chain_offset + gg);
+        YG_CHK(tile, (N + 7) / 8); YG_CHK(gg, N); YG_CHK(s0, s1); YG_CHK(s1 - 1, a.n_steps);
         if (s0 > 0) {      // the transitions before s0 belong to the warp that owns the preceding range: wait for its hand-over
             if (lane == 0) {
                 while (*reinterpret_cast<volatile long long *>(tile_done + tile) != s0) __nanosleep(200);
@@ -417,6 +430,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
         auto slice_begin = [&](const int64_t n, const int j, const int it, const bool on) {
             // a slice index beyond KQ / 2 (more passes than slices) redraws an earlier slice: same values, same place
             const int i_mine = 2 * (it & (KQ / 2 - 1)) + odd;
+            YG_CHK(g * ZS + 4 * i_mine + (t & ~1) + 1, 8 * ZS);
             ns.begin(a.seed, gid, (uint64_t)(a.step0 + n), (uint32_t)j, (uint32_t)((4 * i_mine + (t & ~1)) >> 1),
                      reinterpret_cast<float2 *>(zb + g * ZS + 4 * i_mine + (t & ~1)), on && noise_mode != YG_NOISE_INJECT);
         };
@@ -446,9 +460,11 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
             for (int i = 0; i < KQ; i++) {
                 const int k = 4 * i + t;
                 zv[i] = 0.0;
+                if (noise_mode != YG_NOISE_PHILOX && k < d) YG_CHK(((n * J + j) * d + k) * N + gg, a.n_steps * J * d * N);
                 if (noise_mode == YG_NOISE_INJECT) {
                     if (k < d) zv[i] = a.z[((n * J + j) * d + k) * N + gg];
                 } else if (k < d) {
+                    YG_CHK(g * ZS + k, 8 * ZS);
                     zv[i] = (double)zb[g * ZS + k];
                     if (noise_mode == YG_NOISE_RECORD && live) a.z[((n * J + j) * d + k) * N + gr] = zv[i];
                 }
@@ -463,6 +479,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
 #pragma unroll
                     for (int i = 0; i < KQ; i++)
                         if (4 * i <= nb + 15) dmma_m16n8k4(c0, c1, c2, c3, Lb[4 * i], Lb[(size_t)8 * ks + 4 * i], zv[i]);
+                    YG_CHK((2 * t + 1) * ks + nb + 8 + g, 8 * ks);
                     scr[(2 * t) * ks + nb + g] = c0;
                     scr[(2 * t + 1) * ks + nb + g] = c1;
                     scr[(2 * t) * ks + nb + 8 + g] = c2;
@@ -587,6 +604,7 @@ __global__ void __launch_bounds__(big_max_warps(KQ) * 32, 1) linear_dmma_mh_kern
                 }
                 if (store_now) {
                     const int64_t o = thin_out;
+                    YG_CHK(o, a.n_steps / a.thin);
                     if (a.samples) {
 #pragma unroll 1
                         for (int i = 0; i < KQ; i++)

@@ -86,13 +86,14 @@ YG_DEVFN void tma_stage_blob(void *dst, const void *src, uint32_t bytes, uint64_
 // u / d for 0 <= u < 2^24 via a float reciprocal and one correction step: two integer
 // divisions per work unit were a measurable share of the non-FP64 issue slots.
 // Appends to a shared-memory list with ONE atomic per converged group of lanes.
-YG_DEVFN void list_append(int *list, int *count, int value)
+YG_DEVFN void list_append(int *list, int *count, int value, int limit)
 {
     const unsigned m = __activemask();
     const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
     int base = 0;
     if (lane == leader) base = atomicAdd(count, __popc(m));
     base = __shfl_sync(m, base, leader);
+    YG_CHK(base + __popc(m & ((1u << lane) - 1u)), limit);
     list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     int *nact = reinterpret_cast<int *>(mbar + 1);                         // [2]
     unsigned long long *blk_cnt = reinterpret_cast<unsigned long long *>(mbar + 2);   // [5]
     int *qhead = reinterpret_cast<int *>(mbar + 7);                        // work-queue head of the current phase
+    YG_CHK(reinterpret_cast<unsigned char *>(qhead + 1) - smem_raw - 1, yg_dynamic_smem_bytes());   // the carve-up fits the launch
 
     tma_stage_blob(pb, a.problem, (uint32_t)((a.problem_bytes + 15u) & ~15u), mbar);
     if (tid < 5) blk_cnt[tid] = 0ull;
@@ -149,7 +151,15 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     const double L00 = pb->prop_L[0], L10 = pb->prop_L[LV_D], L11 = pb->prop_L[LV_D + 1];
     const bool pcn = pb->proposal == YG_PROPOSAL_PCN;
 
+#ifdef YG_BOUNDS_CHECK
+    auto ch_at = [&](const int field, const int c) -> double & {
+        YG_CHK(c, cmax);
+        return chain[field * cmax + c];
+    };
+#define CH(field, c) ch_at(SmemLayout::field, (c))
+#else
 #define CH(field, c) chain[(SmemLayout::field) * cmax + (c)]
+#endif
 
     // chains of this CTA: even split of [0, n_chains) over the grid
     const int64_t cta_lo = (a.n_chains * (int64_t)blockIdx.x) / gridDim.x;
@@ -194,7 +204,9 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
             if (lane < batch && u < nUnits) {
                 const int seg = fast_div(u, nItems, inv_items), it = u - seg * nItems;
                 const int n = fast_div(it, na, inv_na), ai = it - n * na;
+                YG_CHK(ai, cmax); YG_CHK(n, nD); YG_CHK(it, nd_max * cmax);
                 const int c = lst[ai];
+                YG_CHK(c, cmax);
                 const LvRates r = lv_rates(h, CH(BETA, c), CH(DELTA, c));
                 double x, y;
                 if (seg == 0) { x = design[2 * n]; y = design[2 * n + 1]; }
@@ -248,6 +260,8 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
     auto draw_z = [&](int c, int64_t g, int64_t n, int j) {
         const uint64_t gid = (uint64_t)(a.chain_offset + g);
         const int64_t zi = ((n * J + j) * LV_D) * N + g;
+        YG_CHK(c, cmax); YG_CHK(g, N);
+        if (a.noise_mode != YG_NOISE_PHILOX) YG_CHK(zi + N, a.n_steps * J * LV_D * N);
         double z0, z1;
         if (a.noise_mode == YG_NOISE_INJECT) {
             z0 = a.z[zi]; z1 = a.z[zi + N];
@@ -261,6 +275,8 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
         const uint64_t gid = (uint64_t)(a.chain_offset + g);
         double *arr = fine ? a.u_f : a.u_c;
         const int64_t i = fine ? n * N + g : (n * J + j) * N + g;
+        YG_CHK(c, cmax); YG_CHK(g, N);
+        if (a.noise_mode != YG_NOISE_PHILOX) YG_CHK(i, fine ? a.n_steps * N : a.n_steps * J * N);
         double u;
         if (a.noise_mode == YG_NOISE_INJECT) u = arr[i];
         else {
@@ -322,6 +338,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
         // ---- load chunk state ---------------------------------------------------
         for (int c = tid; c < C; c += nthr) {
             const int64_t g = cb + c;
+            YG_CHK(g, N);
             CH(TH0, c) = a.theta[g];
             CH(TH1, c) = a.theta[N + g];
             CH(LP0, c) = a.logpost[g];
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                         if (!eq) {
                             CH(BETA, c) = exp(p0);     // LotkaVolterraParameter.evaluate, testSetup.py:57-58
                             CH(DELTA, c) = exp(p1);
-                            list_append(list0 + cur * cmax, &nact[cur], c);
+                            list_append(list0 + cur * cmax, &nact[cur], c, cmax);
                         }
                     } else {
                         // sub-chain finished: s is the MLDA proposal (mlda.py:106-110); a chain whose
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                         if (moved) {
                             CH(BETA, c) = exp(s0);
                             CH(DELTA, c) = exp(s1);
-                            list_append(list0 + cur * cmax, &nact[cur], c);
+                            list_append(list0 + cur * cmax, &nact[cur], c, cmax);
                         }
                     }
                 }
@@ -481,8 +498,10 @@ __global__ void __launch_bounds__(MAXT, 1) lv_mh_kernel(const RunArgs a, const i
                 }
                 if (accepted) { nacc[c] += 1ull; my_acc += 1ull; }
                 if (a.accepted) a.accepted[n * N + g] = accepted ? 1 : 0;
+                YG_CHK(c, cmax); YG_CHK(g, N);
                 if (store_now) {
                     const int64_t o = thin_out;
+                    YG_CHK(o, a.n_steps / a.thin);
                     if (a.samples) {
                         a.samples[(o * LV_D) * N + g] = CH(TH0, c);
                         a.samples[(o * LV_D + 1) * N + g] = CH(TH1, c);
