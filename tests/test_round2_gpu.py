@@ -497,3 +497,62 @@ def test_dmma_short_launches_compose(shape):
         assert torch.equal(sa["theta"], sb["theta"]) and torch.equal(sa["n_accept"], sb["n_accept"])
         np.testing.assert_allclose(sa["w_mean"].cpu().numpy(), sb["w_mean"].cpu().numpy(), rtol=1e-11, atol=1e-14)
         assert a.counters()["transitions"] == b.counters()["transitions"] == 6 * nc
+
+
+# ------------------------------------------------------------------------------------------
+# seeded sweep over problem shapes: every kernel family, ragged sizes, replayed through the oracle
+# ------------------------------------------------------------------------------------------
+def _sweep_case(k):
+    """Configuration k of the sweep (deterministic): (label, meta, arrays, theta0, n_chains, n_steps, thin)."""
+    rng = np.random.default_rng(20261019 + k)
+    fam = ("lv", "small_linear", "big_linear")[k % 3]
+    two = bool(rng.integers(0, 2))
+    J = int(rng.integers(1, 6))
+    nc = int(rng.choice([1, 7, 31, 32, 33, 97, 150, 257, 400]))
+    thin = int(rng.choice([1, 1, 2, 3]))
+    ns = thin * int(rng.integers(2, 9))
+    if fam == "lv":
+        nd = int(rng.choice([1, 2, 3, 5, 10, 17, 40]))
+        Nc, Nf = int(rng.integers(3, 140)), int(rng.integers(130, 420))       # below, at and above one 128-step segment
+        meta, arrays = bp.lv_problem(two, Nc=Nc, Nf=Nf, J=J, n_data=nd, seed=1112 + k)
+        th0 = bp.lv_initial_states(nc)
+        label = f"lv two={two} J={J} n_data={nd} Nc={Nc} Nf={Nf}"
+    else:
+        if fam == "small_linear":        # one chain per thread: every capacity class (2, 4, 8) of d and data_dim
+            d, dd = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        else:                            # FP64 tensor path: d or data_dim beyond 8, up to 64 x 256
+            d, dd = int(rng.integers(9, 65)), int(rng.integers(1, 257))
+            if two:                      # both levels' operands share the SM's shared memory (DESIGN.md 3.3)
+                dd = min(dd, 120 if d > 32 else 240)
+        nd = int(rng.integers(1, 6))
+        meta, arrays = bp.big_linear_problem(d, dd, nd, two_level=two, J=J, seed=3 + k)
+        th0 = 0.1 * rng.standard_normal((nc, d))
+        label = f"{fam} two={two} J={J} d={d} data_dim={dd} n_data={nd}"
+    return f"{label} chains={nc} steps={ns} thin={thin}", meta, arrays, th0, nc, ns, thin
+
+
+@pytest.mark.parametrize("k", range(36))
+def test_seeded_shape_sweep_replayed_through_oracle(k):
+    """Device-drawn noise recorded and replayed through the C oracle on 36 seeded configurations: LV with 1-40 design
+    points and RK4 step counts around the segment length, the one-chain-per-thread linear kernels in every capacity
+    class, the tensor path between 9 x 1 and 64 x 256, one and two levels, sub-chain lengths 1-5, 1-400 chains, thinned
+    output.  Identical accept decisions, trajectories to 1e-12, log-posterior to north_star's 1e-10."""
+    from test_backend_gpu import _replay
+    label, meta, arrays, th0, nc, ns, thin = _sweep_case(k)
+    ens = _ens(meta, arrays, nc, seed=500 + k)
+    ens.set_state(th0)
+    out = ens.run(ns, thin=thin, samples=True, accepted=True, logpost=True, record=True)
+    torch.cuda.synchronize()
+    ref = _replay(meta, arrays, th0, out)
+    acc = out["accepted"].cpu().numpy().T
+    assert int((acc != ref["accepted"]).sum()) == 0, label
+    traj = out["samples"].cpu().numpy().transpose(2, 0, 1)                  # every thin-th state
+    assert traj.shape[1] == ns // thin, label
+    assert rel_err(traj, ref["traj"][:, thin::thin]).max() <= 1e-12, label
+    lp = out["logpost"].cpu().numpy().transpose(2, 0, 1)
+    assert rel_err(lp[:, :, 0], ref["logpost_L0"][:, thin::thin]).max() <= LOGPOST_RTOL, label
+    if meta["levels"] == 2:
+        assert rel_err(lp[:, :, 1], ref["logpost_L1"][:, thin::thin]).max() <= LOGPOST_RTOL, label
+    c = ens.counters()
+    assert c["transitions"] == nc * ns and c["accepted"] == int(acc.sum()), label
+    ens.close()
