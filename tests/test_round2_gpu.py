@@ -506,7 +506,8 @@ def _sweep_case(k):
     """Configuration k of the sweep (deterministic): (label, meta, arrays, theta0, n_chains, n_steps, thin)."""
     rng = np.random.default_rng(20261019 + k)
     fam = ("lv", "small_linear", "big_linear")[k % 3]
-    two = bool(rng.integers(0, 2))
+    feat = ("none", "pcn", "adaptive", "dense")[(k // 3) % 4]
+    two = bool(rng.integers(0, 2)) and feat != "pcn"          # pCN is a single-level method in the reference
     J = int(rng.integers(1, 6))
     nc = int(rng.choice([1, 7, 31, 32, 33, 97, 150, 257, 400]))
     thin = int(rng.choice([1, 1, 2, 3]))
@@ -528,22 +529,39 @@ def _sweep_case(k):
         meta, arrays = bp.big_linear_problem(d, dd, nd, two_level=two, J=J, seed=3 + k)
         th0 = 0.1 * rng.standard_normal((nc, d))
         label = f"{fam} two={two} J={J} d={d} data_dim={dd} n_data={nd}"
-    return f"{label} chains={nc} steps={ns} thin={thin}", meta, arrays, th0, nc, ns, thin
+    # three configurations in four also switch a feature on (the reference's other proposals / covariances)
+    ad = None
+    d = meta["dim"]
+    if feat == "pcn":                                   # chain/method/pcn.py:23-35
+        meta = dict(meta, proposal="pcn", pcn_step=float(rng.uniform(0.002, 0.2)))
+        arrays = dict(arrays, pcn_mean=0.1 * rng.standard_normal(d))
+    elif feat == "adaptive" and d <= 8:                 # chain/adaptive.py:37-64 (per-chain factor: d <= 8)
+        ad = dict(idle=int(rng.integers(1, 5)), collection=int(rng.integers(2, 8)), eps=1e-6, refresh=int(rng.integers(1, 4)))
+    elif feat == "dense" and fam != "lv":               # DenseCovarianceMatrix proposal and prior, covariance.py:69-94
+        A = rng.standard_normal((d, d))
+        cov = A @ A.T / d + 0.5 * np.eye(d)
+        arrays = dict(arrays, prop_L=0.05 * np.linalg.cholesky(cov))
+        prec = np.linalg.inv(2.0 * cov)
+        for l in range(meta["levels"]):
+            arrays[f"L{l}_prior_prec"] = 0.5 * (prec + prec.T)
+    else:
+        feat = "none"
+    return f"{label} {feat} chains={nc} steps={ns} thin={thin}", meta, arrays, th0, nc, ns, thin, ad
 
 
-@pytest.mark.parametrize("k", range(36))
+@pytest.mark.parametrize("k", range(48))
 def test_seeded_shape_sweep_replayed_through_oracle(k):
-    """Device-drawn noise recorded and replayed through the C oracle on 36 seeded configurations: LV with 1-40 design
+    """Device-drawn noise recorded and replayed through the C oracle on 48 seeded configurations: LV with 1-40 design
     points and RK4 step counts around the segment length, the one-chain-per-thread linear kernels in every capacity
     class, the tensor path between 9 x 1 and 64 x 256, one and two levels, sub-chain lengths 1-5, 1-400 chains, thinned
-    output.  Identical accept decisions, trajectories to 1e-12, log-posterior to north_star's 1e-10."""
-    from test_backend_gpu import _replay
-    label, meta, arrays, th0, nc, ns, thin = _sweep_case(k)
-    ens = _ens(meta, arrays, nc, seed=500 + k)
+    output; MRW, pCN, per-chain adaptive Metropolis, dense proposal factor with a dense prior precision.  Identical
+    accept decisions, trajectories to 1e-12, log-posterior to north_star's 1e-10."""
+    label, meta, arrays, th0, nc, ns, thin, ad = _sweep_case(k)
+    ens = _ens(meta, arrays, nc, seed=500 + k, adaptive=ad)
     ens.set_state(th0)
     out = ens.run(ns, thin=thin, samples=True, accepted=True, logpost=True, record=True)
     torch.cuda.synchronize()
-    ref = _replay(meta, arrays, th0, out)
+    ref = _replay(meta, arrays, th0, out, adaptive=ad)
     acc = out["accepted"].cpu().numpy().T
     assert int((acc != ref["accepted"]).sum()) == 0, label
     traj = out["samples"].cpu().numpy().transpose(2, 0, 1)                  # every thin-th state
