@@ -574,3 +574,40 @@ def test_seeded_shape_sweep_replayed_through_oracle(k):
     c = ens.counters()
     assert c["transitions"] == nc * ns and c["accepted"] == int(acc.sum()), label
     ens.close()
+
+
+# ------------------------------------------------------------------------------------------
+# hand-rolled synchronisation of the LV kernel: results must not depend on who runs what when
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("two_level", [True, False])
+def test_lv_results_do_not_depend_on_launch_geometry(two_level):
+    """The LV kernel hands ODE state between warps through shared-memory flags (segments of a long integration), deals
+    work units out through a shared-memory queue and compacts the active chains with atomics: which warp runs which unit,
+    and in which order, changes with the CTA size, the segment length and the number of CTAs per SM -- the results must
+    not.  Eight geometries (1-9 segments per fine integration, 128-1,024 threads, 1-3 CTAs per SM, chunks of 8-443
+    chains), two launches each: samples, accept flags, log-posteriors, Welford moments and counters bit for bit equal.
+    (compute-sanitizer's racecheck is not available on the pool; a race here would show as a geometry dependence.)"""
+    meta, arrays = bp.lv_problem(two_level, Nc=70, Nf=300, J=3, n_data=10)
+    nc, ns = 3001, 6
+    th0 = bp.lv_initial_states(nc)
+    geos = [dict(), dict(threads_per_block=128), dict(threads_per_block=1024, rk4_segment=64), dict(rk4_segment=33),
+            dict(blocks_per_sm=2, threads_per_block=384, rk4_segment=100), dict(blocks_per_sm=3, threads_per_block=256),
+            dict(threads_per_block=512, rk4_segment=300), dict(threads_per_block=640, rk4_segment=17)]
+    ref = None
+    for geo in geos:
+        ens = _ens(meta, arrays, nc, seed=4242, **geo)
+        ens.set_state(th0)
+        ens.run(ns, samples=False)
+        out = ens.run(ns, samples=True, accepted=True, logpost=True)
+        torch.cuda.synchronize()
+        st = ens.state()
+        got = dict(samples=out["samples"].clone(), accepted=out["accepted"].clone(), logpost=out["logpost"].clone(),
+                   w_mean=st["w_mean"].clone(), w_m2=st["w_m2"].clone(), n_accept=st["n_accept"].clone())
+        cnt = {k: v for k, v in ens.counters().items()}
+        if ref is None:
+            ref, ref_cnt = got, cnt
+        else:
+            for k in got:
+                assert torch.equal(got[k], ref[k]), (geo, k)
+            assert cnt == ref_cnt, geo
+        ens.close()
