@@ -584,8 +584,8 @@ def test_lv_results_do_not_depend_on_launch_geometry(two_level):
     """The LV kernel hands ODE state between warps through shared-memory flags (segments of a long integration), deals
     work units out through a shared-memory queue and compacts the active chains with atomics: which warp runs which unit,
     and in which order, changes with the CTA size, the segment length and the number of CTAs per SM -- the results must
-    not.  Eight geometries (1-9 segments per fine integration, 128-1,024 threads, 1-3 CTAs per SM, chunks of 8-443
-    chains), two launches each: samples, accept flags, log-posteriors, Welford moments and counters bit for bit equal.
+    not.  Eight geometries (1-18 segments per fine integration, 128-1,024 threads, 1-3 CTAs per SM, 7-21 chains per
+    CTA), two launches each: samples, accept flags, log-posteriors, Welford moments and counters bit for bit equal.
     (compute-sanitizer's racecheck is not available on the pool; a race here would show as a geometry dependence.)"""
     meta, arrays = bp.lv_problem(two_level, Nc=70, Nf=300, J=3, n_data=10)
     nc, ns = 3001, 6
