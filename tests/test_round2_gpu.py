@@ -579,16 +579,17 @@ def test_seeded_shape_sweep_replayed_through_oracle(k):
 # ------------------------------------------------------------------------------------------
 # hand-rolled synchronisation of the LV kernel: results must not depend on who runs what when
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nc", [3001, 40001])
 @pytest.mark.parametrize("two_level", [True, False])
-def test_lv_results_do_not_depend_on_launch_geometry(two_level):
+def test_lv_results_do_not_depend_on_launch_geometry(two_level, nc):
     """The LV kernel hands ODE state between warps through shared-memory flags (segments of a long integration), deals
     work units out through a shared-memory queue and compacts the active chains with atomics: which warp runs which unit,
     and in which order, changes with the CTA size, the segment length and the number of CTAs per SM -- the results must
-    not.  Eight geometries (1-18 segments per fine integration, 128-1,024 threads, 1-3 CTAs per SM, 7-21 chains per
-    CTA), two launches each: samples, accept flags, log-posteriors, Welford moments and counters bit for bit equal.
+    not.  Eight geometries (1-18 segments per fine integration, 128-1,024 threads, 1-3 CTAs per SM; 7-21 chains per
+    CTA at 3,001 chains, 90-271 at 40,001), two launches each: samples, accept flags, log-posteriors, Welford moments and counters bit for bit equal.
     (compute-sanitizer's racecheck is not available on the pool; a race here would show as a geometry dependence.)"""
     meta, arrays = bp.lv_problem(two_level, Nc=70, Nf=300, J=3, n_data=10)
-    nc, ns = 3001, 6
+    ns = 6
     th0 = bp.lv_initial_states(nc)
     geos = [dict(), dict(threads_per_block=128), dict(threads_per_block=1024, rk4_segment=64), dict(rk4_segment=33),
             dict(blocks_per_sm=2, threads_per_block=384, rk4_segment=100), dict(blocks_per_sm=3, threads_per_block=256),
